@@ -49,7 +49,8 @@ extern "C" {
                                              (patch.cpp:723-761, part of the expansion ctor :36-43) */
 
 /* per-patch status bits (out.status); 0 = nothing unusual */
-#define PMVS_S_TOO_MANY_VIEWS   1u  /* expandVisibleCamera found > PMVS_MAX_VIEWS cameras: patch dropped */
+#define PMVS_S_TOO_MANY_VIEWS      1u  /* expandVisibleCamera found > PMVS_MAX_VIEWS cameras: patch dropped */
+#define PMVS_S_TOO_MANY_PARTICLES  2u  /* TYPE_SEED with 2*particleNum > 64 (patch.cpp:192): patch dropped */
 
 /*
  * Byte-for-byte the reference's MvsConfig (TMVS/mvs/mvs.h:19-72) as laid out by MSVC/gcc x64:
@@ -161,7 +162,8 @@ typedef struct PmvsPatchOut {
     uint16_t camIdx[PMVS_MAX_VIEWS];
     int32_t nImgPoint;        /* imgPoint.size(): set by setImagePoint (patch.cpp:627-653) BEFORE the
                                  trailing removeInvisibleCamera, so it can exceed nCam */
-    int32_t _pad;
+    uint32_t windowEvaluations; /* getFitness calls that walked the whole (2r+1)^2 window, i.e. did not return the
+                                 DBL_MAX sentinel early (patch.cpp:939-962, :999-1002): the gather-traffic unit */
     double  imgPoint[PMVS_MAX_VIEWS][2];
 } PmvsPatchOut;
 
@@ -195,6 +197,14 @@ int pmvs_refine_batch_device(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, Pmvs
 
 /* Number of kernel launches issued by this context so far (bench.py "gpu_launches"). */
 int64_t pmvs_launch_count(const pmvs_ctx *ctx);
+
+/* Test support (not a reference seam): the GLN-PSO solver alone (TMVS/pso/psosolver.cpp) on the analytic functions
+ * 0 sphere, 1 rosenbrock, 3 |x| with a DBL_MAX region, 4 plateaus, so it can be checked bit-for-bit against the
+ * unmodified reference solver. L,U,init: n*3; hasInit,maxIter,P,fn,keys: n. Outputs: gbest n*3, gbestFitness n,
+ * iterations n, particles n*64*8 {pos3,vec3,fitness,pBestFitness} (may be NULL). */
+int pmvs_pso_test(pmvs_ctx *ctx, int n, const double *L, const double *U, const double *init, const int *hasInit,
+                  const int *maxIter, const int *P, const int *fn, const uint64_t *keys, double *gbest,
+                  double *gbestFitness, int *iterations, double *particles);
 
 void pmvs_destroy(pmvs_ctx *ctx);
 const char *pmvs_last_error(const pmvs_ctx *ctx);   /* never NULL; "" when no error */

@@ -605,7 +605,7 @@ struct Patch {
     std::vector<double> corrTable;
     std::vector<double> imgPoint;   /* 2 per entry */
     int psoRuns, psoIterations;
-    uint32_t evals, status;
+    uint32_t evals, status, windowEvals;
     int camNum() const { return (int)camIdx.size(); }
 };
 
@@ -830,10 +830,15 @@ void expandVisibleCamera(const Scene &s, Patch &p) {
     if (p.camNum() < s.cfg.minCamNum) p.drop = true;
 }
 
-struct FitCtx { const Scene *s; PatchView pv; };
+struct FitCtx { const Scene *s; PatchView pv; uint32_t windowEvals; };
 double fitCallback(const double *pos, void *obj) {
     FitCtx *c = (FitCtx *)obj;
-    return getFitness(*c->s, c->pv, pos);
+    const double f = getFitness(*c->s, c->pv, pos);
+    if (f != DBL_MAX) {
+#pragma omp atomic
+        c->windowEvals++;
+    }
+    return f;
 }
 
 /* optional: the UNMODIFIED reference solver (oracle/_ref/libpso_ref.so), registered at run time */
@@ -860,6 +865,7 @@ void psoOptimization(const Scene &s, Patch &p, bool useRefPso, int nThreads) {
     }
     FitCtx ctx;
     ctx.s = &s;
+    ctx.windowEvals = 0;
     memcpy(ctx.pv.ray, p.ray, sizeof(p.ray));
     ctx.pv.refCamIdx = p.refCamIdx;
     ctx.pv.LOD = p.LOD;
@@ -888,6 +894,7 @@ void psoOptimization(const Scene &s, Patch &p, bool useRefPso, int nThreads) {
     for (int k = 0; k < 3; ++k) p.center[k] = p.ray[k] * p.depth + C[k];
     p.psoIterations = iters;
     p.psoRuns++;
+    p.windowEvals += ctx.windowEvals;
 }
 
 /* Patch::refine, patch.cpp:114-176 */
@@ -941,6 +948,7 @@ void patchFromIn(const PmvsPatchIn &in, Patch &p) {   /* AbstractPatch::init, ab
     p.psoIterations = 0;
     p.evals = 0;
     p.status = 0;
+    p.windowEvals = 0;
 }
 
 void patchToOut(const Patch &p, PmvsPatchOut &o) {
@@ -963,6 +971,7 @@ void patchToOut(const Patch &p, PmvsPatchOut &o) {
     o.psoIterations = p.psoIterations;
     o.evaluations = p.evals;
     o.status = p.status;
+    o.windowEvaluations = p.windowEvals;
     for (int i = 0; i < o.nCam; ++i) o.camIdx[i] = p.camIdx[i];
     o.nImgPoint = (int)(p.imgPoint.size() / 2);
     for (int i = 0; i < o.nImgPoint; ++i) { o.imgPoint[i][0] = p.imgPoint[2 * i]; o.imgPoint[i][1] = p.imgPoint[2 * i + 1]; }

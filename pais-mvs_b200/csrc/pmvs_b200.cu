@@ -1,0 +1,637 @@
+/*
+ * pmvs_b200.cu — kernels and the C-ABI (include/pmvs_b200.h) of the B200-native patch-refinement path.
+ *
+ * Kernels:
+ *   pack_quad_kernel      u8 level image -> 4-taps-per-word "quad" layout (see pmvs_device.cuh)
+ *   fitness_batch_kernel  seam 1: one warp = one PAIS::getFitness call (patch.cpp:914-1047)
+ *   refine_kernel         seam 2: persistent CTAs, one CTA = one Patch::refine() (+ trailing removeInvisibleCamera)
+ *   pso_test_kernel       the swarm alone on analytic functions (known-answer tests against the unmodified
+ *                         reference solver)
+ * There is no CPU fallback: every compute entry point needs an sm_100 device.
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pmvs_patch.cuh"
+
+#define PMVS_VERSION "pmvs_b200 0.1 (sm_100a)"
+
+/* ======================================================================================================= */
+__global__ void pack_quad_kernel(const uint8_t *__restrict__ grey, size_t pitch, int cols, int rows, uint32_t *__restrict__ quad) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols || y >= rows) return;
+    const int x1 = min(x + 1, cols - 1), y1 = min(y + 1, rows - 1);
+    const uint32_t g00 = grey[(size_t)y * pitch + x], g01 = grey[(size_t)y * pitch + x1];
+    const uint32_t g10 = grey[(size_t)y1 * pitch + x], g11 = grey[(size_t)y1 * pitch + x1];
+    quad[(size_t)y * cols + x] = g00 | (g01 << 8) | (g10 << 16) | (g11 << 24);
+}
+
+/* carve the dynamic shared memory of one CTA */
+struct SmemPlan {
+    size_t ctaOff, viewOff, distOff, warpOff, corrOff, total;
+    size_t perWarp;      /* doubles per warp: H + xs + ys + dist */
+    int vcap, ps, nWarps;
+};
+static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t headBytes) {
+    SmemPlan pl;
+    pl.vcap = vcap;
+    pl.ps = ps;
+    pl.nWarps = nWarps;
+    size_t off = 0;
+    pl.ctaOff = off;
+    off += (headBytes + 15) & ~(size_t)15;
+    pl.viewOff = off;
+    off += sizeof(ViewS) * (size_t)vcap;
+    off = (off + 15) & ~(size_t)15;
+    pl.distOff = off;
+    off += sizeof(double) * (size_t)ps * ps;
+    pl.warpOff = off;
+    pl.perWarp = (size_t)vcap * 9 + 2 * (size_t)ps + PMVS_MAX_PARTICLES;
+    off += sizeof(double) * pl.perWarp * nWarps;
+    pl.corrOff = off;
+    if (withCorr) off += sizeof(double) * (size_t)vcap * vcap;
+    pl.total = off;
+    return pl;
+}
+struct SmemArgs {
+    unsigned ctaOff, viewOff, distOff, warpOff, corrOff, perWarp;
+    int vcap, ps;
+};
+static SmemArgs to_args(const SmemPlan &pl) {
+    SmemArgs a;
+    a.ctaOff = (unsigned)pl.ctaOff;
+    a.viewOff = (unsigned)pl.viewOff;
+    a.distOff = (unsigned)pl.distOff;
+    a.warpOff = (unsigned)pl.warpOff;
+    a.corrOff = (unsigned)pl.corrOff;
+    a.perWarp = (unsigned)pl.perWarp;
+    a.vcap = pl.vcap;
+    a.ps = pl.ps;
+    return a;
+}
+__device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArgs &a, int warp) {
+    double *base = (double *)(smem + a.warpOff) + (size_t)a.perWarp * warp;
+    WarpWork W;
+    W.H = base;
+    W.xs = base + (size_t)a.vcap * 9;
+    W.ys = W.xs + a.ps;
+    W.dist = W.ys + a.ps;
+    return W;
+}
+
+/* ---- seam 1 ------------------------------------------------------------------------------------------- */
+struct FitWarpS {
+    EvalCtx E;
+};
+__global__ void __launch_bounds__(128) fitness_batch_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
+                                                            const PmvsHypothesis *__restrict__ in, double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    double *sDistW = (double *)(smem + a.distOff);
+    for (int k = tid; k < a.ps * a.ps; k += blockDim.x) sDistW[k] = S.distW[k];
+    /* one EvalCtx + view table per warp: ctaOff holds NW contexts, viewOff NW*vcap views */
+    EvalCtx &E = ((FitWarpS *)(smem + a.ctaOff))[warp].E;
+    if (lane == 0) E.view = (ViewS *)(smem + a.viewOff) + (size_t)warp * a.vcap;
+    __syncthreads();
+    const WarpWork W = warp_work(smem, a, warp);
+    for (int h = blockIdx.x * NW + warp; h < n; h += gridDim.x * NW) {
+        const PmvsHypothesis &hy = in[h];
+        const double ray[3] = {hy.ray[0], hy.ray[1], hy.ray[2]};
+        __syncwarp();
+        build_eval_ctx(S, E, ray, hy.refCamIdx, hy.LOD, hy.nCam, hy.camIdx, lane, 32);
+        __syncwarp();
+        finish_eval_ctx(E, lane);
+        __syncwarp();
+        const double f = warp_fitness_any(S, E, sDistW, W, hy.theta, hy.phi, hy.depth);
+        if (lane == 0) out[h] = f;
+    }
+}
+
+/* ---- seam 2 ------------------------------------------------------------------------------------------- */
+__device__ inline void patch_from_in(const PmvsPatchIn &in, PatchS &p) {   /* AbstractPatch::init, abstractpatch.cpp:25-40 */
+    for (int k = 0; k < 3; ++k) {
+        p.center[k] = in.center[k];
+        p.normal[k] = in.normal[k];
+        p.ray[k] = 0;
+    }
+    p.normalS[0] = in.normalS[0];
+    p.normalS[1] = in.normalS[1];
+    p.depth = 0;
+    p.depthRange[0] = p.depthRange[1] = 0;
+    p.fitness = DBL_MAX;
+    p.priority = DBL_MAX;
+    p.correlation = 0;
+    p.LOD = -1;
+    p.refCamIdx = -1;
+    p.type = in.type;
+    p.id = in.id;
+    p.drop = 0;
+    int n = in.nCam;
+    n = n < 0 ? 0 : (n > PMVS_MAX_VIEWS ? PMVS_MAX_VIEWS : n);
+    p.nCam = n;
+    for (int i = 0; i < n; ++i) p.camIdx[i] = in.camIdx[i];
+    p.psoRuns = 0;
+    p.psoIterations = 0;
+    p.nImgPoint = 0;
+    p.evals = 0;
+    p.status = 0;
+    p.windowEvals = 0;
+    p.flag = 0;
+}
+__device__ inline void patch_to_out(const PatchS &p, PmvsPatchOut &o) {
+    for (int k = 0; k < 3; ++k) {
+        o.center[k] = p.center[k];
+        o.normal[k] = p.normal[k];
+        o.ray[k] = p.ray[k];
+    }
+    o.normalS[0] = p.normalS[0];
+    o.normalS[1] = p.normalS[1];
+    o.depth = p.depth;
+    o.depthRange[0] = p.depthRange[0];
+    o.depthRange[1] = p.depthRange[1];
+    o.fitness = p.fitness;
+    o.priority = p.priority;
+    o.correlation = p.correlation;
+    o.LOD = p.LOD;
+    o.refCamIdx = p.refCamIdx;
+    o.nCam = p.nCam;
+    o.drop = p.drop ? 1 : 0;
+    o.psoRuns = p.psoRuns;
+    o.psoIterations = p.psoIterations;
+    o.evaluations = p.evals;
+    o.status = p.status;
+    o.windowEvaluations = p.windowEvals;
+    for (int i = 0; i < p.nCam; ++i) o.camIdx[i] = p.camIdx[i];
+    o.nImgPoint = p.nImgPoint;
+    for (int i = 0; i < p.nImgPoint; ++i) {
+        o.imgPoint[i][0] = p.imgPoint[i][0];
+        o.imgPoint[i][1] = p.imgPoint[i][1];
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) refine_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
+                                                        const PmvsPatchIn *__restrict__ in, PmvsPatchOut *__restrict__ out,
+                                                        uint32_t flags, int *__restrict__ counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    CtaS &c = *(CtaS *)(smem + a.ctaOff);
+    double *sDistW = (double *)(smem + a.distOff);
+    double *corr = (double *)(smem + a.corrOff);
+    for (int k = tid; k < a.ps * a.ps; k += blockDim.x) sDistW[k] = S.distW[k];
+    if (tid == 0) c.E.view = (ViewS *)(smem + a.viewOff);
+    const WarpWork W = warp_work(smem, a, warp);
+    const WarpWork W0 = warp_work(smem, a, 0);
+    double *hp = S.scratch + (size_t)S.scratchStride * blockIdx.x;
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) c.nextIdx = atomicAdd(counter, 1);
+        __syncthreads();
+        const int idx = c.nextIdx;
+        if (idx >= n) break;
+        if (tid == 0) {
+            patch_from_in(in[idx], c.p);
+            if (c.p.type == PMVS_TYPE_SEED && S.cfg.particleNum * 2 > PMVS_MAX_PARTICLES) {   /* patch.cpp:192 needs 2P particles */
+                c.p.status |= PMVS_S_TOO_MANY_PARTICLES;
+                c.p.drop = 1;
+            }
+        }
+        __syncthreads();
+        if (!(c.p.status & PMVS_S_TOO_MANY_PARTICLES)) {
+            if ((flags & PMVS_F_EXPAND_VISIBLE) && c.p.type == PMVS_TYPE_EXPAND) cta_expand_visible(S, c.p);
+            cta_refine(S, c, sDistW, W, W0.H, W0.xs, W0.ys, corr, hp);
+            __syncthreads();
+            if (flags & PMVS_F_POST_REMOVE_INVISIBLE) cta_remove_invisible(S, c, W0.H, W0.xs, W0.ys, corr, hp);   /* mvs.cpp:215, :574 */
+        }
+        __syncthreads();
+        /* assemble the record in shared memory, then store it with coalesced 32-bit words */
+        uint32_t *ow = (uint32_t *)&c.out;
+        for (int k = tid; k < (int)(sizeof(PmvsPatchOut) / 4); k += blockDim.x) ow[k] = 0;
+        __syncthreads();
+        if (tid == 0) patch_to_out(c.p, c.out);
+        __syncthreads();
+        uint32_t *gw = (uint32_t *)(out + idx);
+        for (int k = tid; k < (int)(sizeof(PmvsPatchOut) / 4); k += blockDim.x) gw[k] = ow[k];
+        __syncthreads();
+    }
+}
+
+/* ---- swarm on analytic functions (test support) ------------------------------------------------------- */
+struct TestEval {
+    int fn;
+    __device__ __forceinline__ double operator()(const double *x) const {
+        switch (fn) {
+        default:
+        case 0: return (x[0] - 0.3) * (x[0] - 0.3) + (x[1] + 0.2) * (x[1] + 0.2) + (x[2] - 1.5) * (x[2] - 1.5);
+        case 1: {
+            double aa = x[1] - x[0] * x[0], b = 1 - x[0], cc = x[2] - x[1] * x[1], d = 1 - x[1];
+            return 100 * aa * aa + b * b + 100 * cc * cc + d * d;
+        }
+        case 3: return (x[0] > 0.5) ? DBL_MAX : fabs(x[0]) + fabs(x[1]) + fabs(x[2]);
+        case 4: return floor(4 * fabs(x[0])) + floor(4 * fabs(x[1])) + floor(4 * fabs(x[2]));
+        }
+    }
+};
+struct PsoTestS {
+    PsoS pso;
+    ParticleS part[PMVS_MAX_PARTICLES];
+    double dist[16][PMVS_MAX_PARTICLES];
+    double init[3];
+};
+/* one CTA per problem; io = per problem {L3,U3,init3,hasInit,maxIter,P,fn,key(as 2 doubles via bits)} */
+struct PsoTestProblem {
+    double L[3], U[3], init[3];
+    uint64_t key;
+    int hasInit, maxIter, P, fn;
+};
+struct PsoTestResult {
+    double gbest[3], gbestFitness;
+    int iterations, _pad;
+    double particles[PMVS_MAX_PARTICLES][8];
+};
+__global__ void __launch_bounds__(512) pso_test_kernel(int n, const PsoTestProblem *__restrict__ prob, PsoTestResult *__restrict__ res) {
+    __shared__ PsoTestS s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const PsoTestProblem &pr = prob[b];
+        if (tid == 0) {
+            pso_setup(s.pso, pr.L, pr.U, pr.maxIter, pr.P, pr.key);
+            for (int d = 0; d < 3; ++d) s.init[d] = pr.init[d];
+        }
+        __syncthreads();
+        TestEval ev = {pr.fn};
+        pso_run(s.pso, s.part, s.dist[warp], ev, s.init, pr.hasInit != 0);
+        if (tid == 0) {
+            PsoTestResult &r = res[b];
+            const ParticleS &g = s.part[s.pso.gBestIdx];
+            for (int d = 0; d < 3; ++d) r.gbest[d] = g.pBest[d];
+            r.gbestFitness = s.pso.gBestFitness;
+            r.iterations = s.pso.iteration;
+            for (int i = 0; i < pr.P; ++i) {
+                const ParticleS &q = s.part[i];
+                for (int d = 0; d < 3; ++d) {
+                    r.particles[i][d] = q.pos[d];
+                    r.particles[i][3 + d] = q.vec[d];
+                }
+                r.particles[i][6] = q.fitness;
+                r.particles[i][7] = q.pbf;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* =======================================================================================================
+ * host side: context + C-ABI
+ * ===================================================================================================== */
+struct pmvs_ctx {
+    int device = -1;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    PmvsConfig cfg;
+    int nCams = 0;
+    int vcap = 0;
+    uint64_t seed = 0;
+    std::vector<void *> allocs;          /* pyramid storage */
+    DevCamera *dCams = nullptr;
+    double *dDistW = nullptr;
+    double *dScratch = nullptr;
+    size_t scratchStride = 0;
+    int scratchCtas = 0;
+    int *dCounter = nullptr;
+    void *dIn = nullptr, *dOut = nullptr;
+    size_t dInBytes = 0, dOutBytes = 0;
+    int64_t launches = 0;
+    std::string err;
+    DevScene scene;
+};
+
+static int fail(pmvs_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? PMVS_E_NOMEM : PMVS_E_CUDA,                \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+    } while (0)
+
+/* MVS::initPatchDistanceWeighting, mvs.cpp:97-114 */
+static std::vector<double> dist_weight(const PmvsConfig &cfg) {
+    const int ps = cfg.patchSize, r = cfg.patchRadius;
+    std::vector<double> w((size_t)ps * ps);
+    const double sigma = cfg.distWeighting;
+    const double s2 = 1.0 / (2.0 * sigma * sigma);
+    const double s = 1.0 / (2.0 * M_PI * sigma * sigma);
+    for (int x = 0; x < ps; ++x)
+        for (int y = 0; y < ps; ++y) {
+            const double e = -(pow((double)(x - r), 2) + pow((double)(y - r), 2)) * s2;
+            w[(size_t)x * ps + y] = s * exp(e);
+        }
+    double n = 0;
+    for (size_t i = 0; i < w.size(); ++i) n += w[i];
+    for (size_t i = 0; i < w.size(); ++i) w[i] = w[i] / n;
+    return w;
+}
+
+static int check_config(pmvs_ctx *ctx, const PmvsConfig &cfg) {
+    if (cfg.patchRadius < 0 || cfg.patchRadius > PMVS_MAX_RADIUS)
+        return fail(ctx, PMVS_E_UNSUPPORTED, "patchRadius must be in [0, " + std::to_string(PMVS_MAX_RADIUS) + "]");
+    if (cfg.particleNum < 1 || cfg.particleNum > PMVS_MAX_PARTICLES)
+        return fail(ctx, PMVS_E_UNSUPPORTED, "particleNum must be in [1, " + std::to_string(PMVS_MAX_PARTICLES) + "]");
+    if (cfg.maxIteration < 0) return fail(ctx, PMVS_E_ARG, "maxIteration < 0");
+    if (!(cfg.lodRatio > 0.0 && cfg.lodRatio <= 1.0)) return fail(ctx, PMVS_E_ARG, "lodRatio must be in (0,1]");
+    return PMVS_OK;
+}
+
+static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
+    int rc = check_config(ctx, *cfg);
+    if (rc) return rc;
+    ctx->cfg = *cfg;
+    ctx->cfg.patchSize = (cfg->patchRadius << 1) + 1;                               /* mvs.cpp:67 */
+    const std::vector<double> w = dist_weight(ctx->cfg);
+    if (ctx->dDistW) { cudaFree(ctx->dDistW); ctx->dDistW = nullptr; }
+    CK(cudaMalloc(&ctx->dDistW, w.size() * sizeof(double)));
+    CK(cudaMemcpy(ctx->dDistW, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+    DevScene &s = ctx->scene;
+    s.cfg = ctx->cfg;
+    s.cams = ctx->dCams;
+    s.distW = ctx->dDistW;
+    s.nCams = ctx->nCams;
+    s.seed = ctx->seed;
+    for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
+    /* correlation scratch: one slab per resident CTA */
+    const size_t stride = (size_t)ctx->vcap * ctx->cfg.patchSize * ctx->cfg.patchSize;
+    const int ctas = ctx->smCount * 2;
+    if (stride > ctx->scratchStride || ctas > ctx->scratchCtas || !ctx->dScratch) {
+        if (ctx->dScratch) cudaFree(ctx->dScratch);
+        ctx->dScratch = nullptr;
+        CK(cudaMalloc(&ctx->dScratch, stride * ctas * sizeof(double)));
+        ctx->scratchStride = stride;
+        ctx->scratchCtas = ctas;
+    }
+    s.scratch = ctx->dScratch;
+    s.scratchStride = ctx->scratchStride;
+    return PMVS_OK;
+}
+
+extern "C" {
+
+const char *pmvs_version(void) { return PMVS_VERSION; }
+const char *pmvs_last_error(const pmvs_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+int64_t pmvs_launch_count(const pmvs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void pmvs_destroy(pmvs_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->device >= 0) cudaSetDevice(ctx->device);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->dCams) cudaFree(ctx->dCams);
+    if (ctx->dDistW) cudaFree(ctx->dDistW);
+    if (ctx->dScratch) cudaFree(ctx->dScratch);
+    if (ctx->dCounter) cudaFree(ctx->dCounter);
+    if (ctx->dIn) cudaFree(ctx->dIn);
+    if (ctx->dOut) cudaFree(ctx->dOut);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int create_impl(pmvs_ctx *ctx, const PmvsConfig *cfg, int nCams, const PmvsCamera *cams, int device, uint64_t rngSeed) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(ctx, PMVS_E_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                                          " (this library has no CPU path)");
+    if (device < 0 || device >= count) return fail(ctx, PMVS_E_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ctx, PMVS_E_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                          std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    ctx->device = device;
+    ctx->smCount = prop.multiProcessorCount;
+    ctx->seed = rngSeed;
+    ctx->nCams = nCams;
+    ctx->vcap = nCams < PMVS_MAX_VIEWS ? nCams : PMVS_MAX_VIEWS;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&ctx->dCounter, sizeof(int)));
+
+    std::vector<DevCamera> hc(nCams);
+    for (int i = 0; i < nCams; ++i) {
+        const PmvsCamera &c = cams[i];
+        DevCamera &d = hc[i];
+        memset(&d, 0, sizeof(d));
+        memcpy(d.center, c.center, sizeof(d.center));
+        memcpy(d.R, c.R, sizeof(d.R));
+        memcpy(d.t, c.t, sizeof(d.t));
+        memcpy(d.KR, c.KR, sizeof(d.KR));
+        memcpy(d.KT, c.KT, sizeof(d.KT));
+        memcpy(d.optN, c.opticalNormal, sizeof(d.optN));
+        memcpy(d.focal, c.focal, sizeof(d.focal));
+        memcpy(d.pp, c.principal, sizeof(d.pp));
+        if (c.maxLOD < 0 || c.maxLOD >= PMVS_MAX_LEVELS) return fail(ctx, PMVS_E_ARG, "camera maxLOD out of range");
+        d.maxLOD = c.maxLOD;
+        for (int l = 0; l <= c.maxLOD; ++l) {
+            const PmvsLevel &L = c.level[l];
+            if (L.cols <= 0 || L.rows <= 0 || !L.grey || L.pitch < L.cols) return fail(ctx, PMVS_E_ARG, "bad pyramid level");
+            uint8_t *tmp = nullptr;
+            uint32_t *quad = nullptr;
+            size_t dpitch = 0;
+            CK(cudaMallocPitch(&tmp, &dpitch, (size_t)L.cols, (size_t)L.rows));
+            e = cudaMalloc(&quad, (size_t)L.cols * L.rows * sizeof(uint32_t));
+            if (e != cudaSuccess) { cudaFree(tmp); return fail(ctx, PMVS_E_NOMEM, "cudaMalloc(quad level) failed"); }
+            ctx->allocs.push_back(quad);
+            e = cudaMemcpy2DAsync(tmp, dpitch, L.grey, (size_t)L.pitch, (size_t)L.cols, (size_t)L.rows, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) {
+                dim3 grid((L.cols + 255) / 256, L.rows);
+                pack_quad_kernel<<<grid, 256, 0, ctx->stream>>>(tmp, dpitch, L.cols, L.rows, quad);
+                ctx->launches++;
+                e = cudaStreamSynchronize(ctx->stream);
+            }
+            cudaFree(tmp);
+            if (e != cudaSuccess) return fail(ctx, PMVS_E_CUDA, std::string("level upload: ") + cudaGetErrorString(e));
+            d.level[l].quad = quad;
+            d.level[l].cols = L.cols;
+            d.level[l].rows = L.rows;
+            d.level[l].edge = nullptr;
+            if (L.edge) {
+                double *edge = nullptr;
+                CK(cudaMalloc(&edge, (size_t)L.cols * L.rows * sizeof(double)));
+                ctx->allocs.push_back(edge);
+                CK(cudaMemcpy(edge, L.edge, (size_t)L.cols * L.rows * sizeof(double), cudaMemcpyHostToDevice));
+                d.level[l].edge = edge;
+            }
+        }
+    }
+    CK(cudaMalloc(&ctx->dCams, sizeof(DevCamera) * (size_t)nCams));
+    CK(cudaMemcpy(ctx->dCams, hc.data(), sizeof(DevCamera) * (size_t)nCams, cudaMemcpyHostToDevice));
+    return apply_config(ctx, cfg);
+}
+
+int pmvs_create(pmvs_ctx **out, const PmvsConfig *cfg, int nCams, const PmvsCamera *cams, int device, uint64_t rngSeed) {
+    if (!out) return PMVS_E_ARG;
+    *out = nullptr;
+    pmvs_ctx *ctx = new (std::nothrow) pmvs_ctx();
+    if (!ctx) return PMVS_E_NOMEM;
+    *out = ctx;      /* returned even on failure so pmvs_last_error() can explain; caller destroys it */
+    if (!cfg || !cams || nCams <= 0 || nCams > 65535) return fail(ctx, PMVS_E_ARG, "bad arguments to pmvs_create");
+    return create_impl(ctx, cfg, nCams, cams, device, rngSeed);
+}
+
+int pmvs_set_neighbor_radius(pmvs_ctx *ctx, double neighborRadius) {
+    if (!ctx || ctx->device < 0) return PMVS_E_ARG;
+    ctx->cfg.neighborRadius = neighborRadius;
+    ctx->scene.cfg.neighborRadius = neighborRadius;
+    return PMVS_OK;
+}
+
+int pmvs_set_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
+    if (!ctx || !cfg || ctx->device < 0) return PMVS_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return apply_config(ctx, cfg);
+}
+
+static int ensure_buffers(pmvs_ctx *ctx, size_t inBytes, size_t outBytes) {
+    if (inBytes > ctx->dInBytes) {
+        if (ctx->dIn) cudaFree(ctx->dIn);
+        ctx->dIn = nullptr;
+        ctx->dInBytes = 0;
+        CK(cudaMalloc(&ctx->dIn, inBytes));
+        ctx->dInBytes = inBytes;
+    }
+    if (outBytes > ctx->dOutBytes) {
+        if (ctx->dOut) cudaFree(ctx->dOut);
+        ctx->dOut = nullptr;
+        ctx->dOutBytes = 0;
+        CK(cudaMalloc(&ctx->dOut, outBytes));
+        ctx->dOutBytes = outBytes;
+    }
+    return PMVS_OK;
+}
+
+int pmvs_fitness_batch(pmvs_ctx *ctx, int n, const PmvsHypothesis *in, double *outFitness) {
+    if (!ctx || ctx->device < 0) return PMVS_E_ARG;
+    if (n < 0 || (n > 0 && (!in || !outFitness))) return fail(ctx, PMVS_E_ARG, "bad arguments to pmvs_fitness_batch");
+    if (n == 0) return PMVS_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_buffers(ctx, sizeof(PmvsHypothesis) * (size_t)n, sizeof(double) * (size_t)n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->dIn, in, sizeof(PmvsHypothesis) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    const int NW = 4;
+    SmemPlan pl = plan_smem(PMVS_MAX_VIEWS * NW, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW);
+    /* the per-warp H area must hold PMVS_MAX_VIEWS homographies: plan with vcap = MAX_VIEWS for the warp area */
+    SmemPlan plw = plan_smem(PMVS_MAX_VIEWS, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW);
+    pl.perWarp = plw.perWarp;
+    pl.total = pl.warpOff + sizeof(double) * pl.perWarp * NW;
+    SmemArgs a = to_args(pl);
+    a.vcap = PMVS_MAX_VIEWS;
+    CK(cudaFuncSetAttribute(fitness_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+    int grid = (n + NW - 1) / NW;
+    if (grid > ctx->smCount * 8) grid = ctx->smCount * 8;
+    fitness_batch_kernel<<<grid, NW * 32, pl.total, ctx->stream>>>(ctx->scene, a, n, (const PmvsHypothesis *)ctx->dIn, (double *)ctx->dOut);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(outFitness, ctx->dOut, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PMVS_OK;
+}
+
+static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatchOut *d_out, uint32_t flags, cudaStream_t st) {
+    const int maxP = ctx->cfg.particleNum;      /* seeds run 2P particles in rounds over the same warps */
+    const int NW = maxP < 4 ? 4 : (maxP > 16 ? 16 : maxP);
+    SmemPlan pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, sizeof(CtaS));
+    CK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+    int perSm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, refine_kernel, NW * 32, pl.total));
+    if (perSm < 1) return fail(ctx, PMVS_E_UNSUPPORTED, "refine kernel does not fit on an SM with this configuration");
+    if (perSm > 2) perSm = 2;
+    int grid = ctx->smCount * perSm;
+    if (grid > ctx->scratchCtas) grid = ctx->scratchCtas;
+    if (grid > n) grid = n;
+    CK(cudaMemsetAsync(ctx->dCounter, 0, sizeof(int), st));
+    refine_kernel<<<grid, NW * 32, pl.total, st>>>(ctx->scene, to_args(pl), n, d_in, d_out, flags, ctx->dCounter);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PMVS_OK;
+}
+
+int pmvs_refine_batch_device(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatchOut *d_out, uint32_t flags, void *cudaStream) {
+    if (!ctx || ctx->device < 0) return PMVS_E_ARG;
+    if (n < 0 || (n > 0 && (!d_in || !d_out))) return fail(ctx, PMVS_E_ARG, "bad arguments to pmvs_refine_batch_device");
+    if (n == 0) return PMVS_OK;
+    CK(cudaSetDevice(ctx->device));
+    return refine_launch(ctx, n, d_in, d_out, flags, cudaStream ? (cudaStream_t)cudaStream : ctx->stream);
+}
+
+int pmvs_refine_batch(pmvs_ctx *ctx, int n, const PmvsPatchIn *in, PmvsPatchOut *out, uint32_t flags) {
+    if (!ctx || ctx->device < 0) return PMVS_E_ARG;
+    if (n < 0 || (n > 0 && (!in || !out))) return fail(ctx, PMVS_E_ARG, "bad arguments to pmvs_refine_batch");
+    if (n == 0) return PMVS_OK;
+    if (ctx->cfg.particleNum * 2 > PMVS_MAX_PARTICLES)
+        for (int i = 0; i < n; ++i)
+            if (in[i].type == PMVS_TYPE_SEED)
+                return fail(ctx, PMVS_E_UNSUPPORTED, "seed patches need 2*particleNum <= " + std::to_string(PMVS_MAX_PARTICLES));
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_buffers(ctx, sizeof(PmvsPatchIn) * (size_t)n, sizeof(PmvsPatchOut) * (size_t)n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->dIn, in, sizeof(PmvsPatchIn) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = refine_launch(ctx, n, (const PmvsPatchIn *)ctx->dIn, (PmvsPatchOut *)ctx->dOut, flags, ctx->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->dOut, sizeof(PmvsPatchOut) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PMVS_OK;
+}
+
+/* test support: the swarm alone on analytic functions. L,U,init: n*3; keys,maxIter,P,fn,hasInit: n. Outputs:
+ * gbest n*3, gbestFitness n, iterations n, particles n*64*8 (may be NULL). */
+int pmvs_pso_test(pmvs_ctx *ctx, int n, const double *L, const double *U, const double *init, const int *hasInit,
+                  const int *maxIter, const int *P, const int *fn, const uint64_t *keys, double *gbest, double *gbestFitness,
+                  int *iterations, double *particles) {
+    if (!ctx || ctx->device < 0 || n <= 0) return PMVS_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<PsoTestProblem> pr(n);
+    for (int i = 0; i < n; ++i) {
+        if (P[i] < 1 || P[i] > PMVS_MAX_PARTICLES) return fail(ctx, PMVS_E_UNSUPPORTED, "P out of range");
+        for (int d = 0; d < 3; ++d) {
+            pr[i].L[d] = L[3 * i + d];
+            pr[i].U[d] = U[3 * i + d];
+            pr[i].init[d] = init ? init[3 * i + d] : 0.0;
+        }
+        pr[i].key = keys[i];
+        pr[i].hasInit = hasInit ? hasInit[i] : 0;
+        pr[i].maxIter = maxIter[i];
+        pr[i].P = P[i];
+        pr[i].fn = fn[i];
+    }
+    PsoTestProblem *dp = nullptr;
+    PsoTestResult *dr = nullptr;
+    CK(cudaMalloc(&dp, sizeof(PsoTestProblem) * n));
+    cudaError_t e = cudaMalloc(&dr, sizeof(PsoTestResult) * n);
+    if (e != cudaSuccess) { cudaFree(dp); return fail(ctx, PMVS_E_NOMEM, "cudaMalloc failed"); }
+    std::vector<PsoTestResult> hr(n);
+    e = cudaMemcpy(dp, pr.data(), sizeof(PsoTestProblem) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        pso_test_kernel<<<n < 1024 ? n : 1024, 512, 0, ctx->stream>>>(n, dp, dr);
+        ctx->launches++;
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(hr.data(), dr, sizeof(PsoTestResult) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dp);
+    cudaFree(dr);
+    if (e != cudaSuccess) return fail(ctx, PMVS_E_CUDA, std::string("pso_test: ") + cudaGetErrorString(e));
+    for (int i = 0; i < n; ++i) {
+        for (int d = 0; d < 3; ++d) gbest[3 * i + d] = hr[i].gbest[d];
+        gbestFitness[i] = hr[i].gbestFitness;
+        iterations[i] = hr[i].iterations;
+        if (particles) memcpy(particles + (size_t)i * PMVS_MAX_PARTICLES * 8, hr[i].particles, sizeof(hr[i].particles));
+    }
+    return PMVS_OK;
+}
+
+}   // extern "C"

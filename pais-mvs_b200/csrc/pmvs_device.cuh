@@ -1,0 +1,648 @@
+/*
+ * pmvs_device.cuh — device-side data layout and the warp-/CTA-cooperative building blocks of the patch
+ * refinement path (sm_100a). Compiled with -fmad=false: every a*b+c below is two roundings, like the reference
+ * (MSVC /fp:precise) — fused multiply-adds appear only where fma() is written out (the sample loop).
+ *
+ * Reference functions restated here (paths relative to the reference tree, TMVS/):
+ *   mvs/camera.cpp:138-160  Camera::project            -> project_pt
+ *   mvs/patch.cpp:290-330   Patch::getHomographies     -> warp_homographies
+ *   mvs/patch.cpp:914-1047  PAIS::getFitness           -> warp_fitness
+ *   pso/psosolver.cpp       PsoSolver (whole file)     -> pso_run / warp_move
+ *
+ * HBM layout. Every pyramid level of every camera is stored as a "quad" image: one 32-bit word per pixel (x,y)
+ * holding the four bilinear taps g(y,x) | g(y,x+1)<<8 | g(y+1,x)<<16 | g(y+1,x+1)<<24 (edge-replicated). The
+ * reference issues four byte loads per sample and view (patch.cpp:1014-1017); here that is ONE aligned 32-bit
+ * load, coalesced across the warp because lanes walk the window along x. It costs 4 B/pixel of the 180 GB HBM
+ * (config 5: 64 views x 12 MP x 2.8 levels x 4 B = 8.6 GB) and needs no per-patch staging pass.
+ */
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/pmvs_b200.h"
+#include "pmvs_rng.h"
+
+#define PMVS_MAX_PARTICLES 64
+#define PMVS_MAX_RADIUS 31
+#define PMVS_MAX_PS (2 * PMVS_MAX_RADIUS + 1)
+#define PMVS_FULL 0xffffffffu
+
+struct DevLevel {
+    const uint32_t *quad;
+    const double *edge;
+    int cols, rows;
+};
+struct DevCamera {
+    double center[3], R[9], t[3], KR[9], KT[3], optN[3], focal[2], pp[2];
+    int maxLOD, _pad;
+    DevLevel level[PMVS_MAX_LEVELS];
+};
+struct DevScene {
+    PmvsConfig cfg;
+    const DevCamera *cams;
+    const double *distW;       /* patchSize^2, index x*patchSize+y (mvs.cpp:104-109) */
+    double *scratch;           /* per-CTA correlation windows: scratchStride doubles per CTA */
+    unsigned long long scratchStride;
+    int nCams, _pad;
+    uint64_t seed;
+    double lodScale[PMVS_MAX_LEVELS];
+};
+
+/* ---- per-patch evaluation context (shared memory, read-only while the swarm runs) ---------------------- */
+struct ViewS {
+    double KR[9], KT[3];
+    const uint32_t *quad;
+    int cols, rows, isRef, _pad;
+};
+struct EvalCtx {
+    double ray[3], refC[3], refOptN[3], refR[9], refT[3], refKR[9], refKT[3], refFocal[2], refPP[2], sc;
+    const uint32_t *refQuad;
+    const double *refEdge;
+    ViewS *view;
+    int refCols, refRows, refCam, LOD, V, valid;
+};
+/* per-warp scratch (shared memory) */
+struct WarpWork {
+    double *H;      /* V*9 */
+    double *xs;     /* patchSize */
+    double *ys;     /* patchSize */
+    double *dist;   /* PMVS_MAX_PARTICLES */
+};
+
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+/* Utility::spherical2Normal, mvs/utility.h:25-29 */
+__device__ __forceinline__ void spherical2Normal(double theta, double phi, double *n) {
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct);
+    sincos(phi, &sp, &cp);
+    n[0] = st * cp;
+    n[1] = st * sp;
+    n[2] = ct;
+}
+
+/* Camera::project without distortion (camera.cpp:138-160); the in-image test is the caller's. */
+__device__ __forceinline__ void project_pt(const double *R, const double *t, const double *focal, const double *pp, double sc,
+                                           const double *X, double *out) {
+    double x2 = (R[0] * X[0] + R[1] * X[1] + R[2] * X[2]) + t[0];
+    double y2 = (R[3] * X[0] + R[4] * X[1] + R[5] * X[2]) + t[1];
+    double z2 = (R[6] * X[0] + R[7] * X[1] + R[8] * X[2]) + t[2];
+    out[0] = focal[0] * (x2 / z2);
+    out[1] = focal[1] * (y2 / z2);
+    out[0] += pp[0];
+    out[1] += pp[1];
+    out[0] *= sc;
+    out[1] *= sc;
+}
+/* Camera::inImage(Vec2d), camera.h:116-131 */
+__device__ __forceinline__ bool in_image(double x, double y, int cols, int rows) {
+    if (isnan(x) || isnan(y)) return false;
+    return !(x < 0 || x >= cols || y < 0 || y >= rows);
+}
+
+/* OpenCV 2.4 cv::invert, 3x3 CV_64F closed form (used by Mat_::inv() at patch.cpp:314) */
+__device__ __forceinline__ void inv3(const double *S, double *D) {
+#define Sd(r, c) S[(r)*3 + (c)]
+    double d = Sd(0, 0) * (Sd(1, 1) * Sd(2, 2) - Sd(1, 2) * Sd(2, 1)) - Sd(0, 1) * (Sd(1, 0) * Sd(2, 2) - Sd(1, 2) * Sd(2, 0)) +
+               Sd(0, 2) * (Sd(1, 0) * Sd(2, 1) - Sd(1, 1) * Sd(2, 0));
+    if (d != 0.) {
+        d = 1. / d;
+        D[0] = (Sd(1, 1) * Sd(2, 2) - Sd(1, 2) * Sd(2, 1)) * d;
+        D[1] = (Sd(0, 2) * Sd(2, 1) - Sd(0, 1) * Sd(2, 2)) * d;
+        D[2] = (Sd(0, 1) * Sd(1, 2) - Sd(0, 2) * Sd(1, 1)) * d;
+        D[3] = (Sd(1, 2) * Sd(2, 0) - Sd(1, 0) * Sd(2, 2)) * d;
+        D[4] = (Sd(0, 0) * Sd(2, 2) - Sd(0, 2) * Sd(2, 0)) * d;
+        D[5] = (Sd(0, 2) * Sd(1, 0) - Sd(0, 0) * Sd(1, 2)) * d;
+        D[6] = (Sd(1, 0) * Sd(2, 1) - Sd(1, 1) * Sd(2, 0)) * d;
+        D[7] = (Sd(0, 1) * Sd(2, 0) - Sd(0, 0) * Sd(2, 1)) * d;
+        D[8] = (Sd(0, 0) * Sd(1, 1) - Sd(0, 1) * Sd(1, 0)) * d;
+    } else {
+        for (int i = 0; i < 9; ++i) D[i] = 0;
+    }
+#undef Sd
+}
+
+/* d*L*KR - L*KT*n^T, L = diag(s,s,1): the bracket of patch.cpp:314 / :328 */
+__device__ __forceinline__ void plane_matrix(const double *KR, const double *KT, const double *n, double d, double sc, double *M) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double L = (r < 2) ? sc : 1.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) M[r * 3 + c] = d * (L * KR[r * 3 + c]) - (L * KT[r]) * n[c];
+    }
+}
+
+/* Patch::getHomographies (patch.cpp:290-330): lane v builds H_v (ref -> view v) in f64 and stores it in Hw[9v..]. */
+__device__ __forceinline__ void warp_homographies(const EvalCtx &E, const double *center, const double *normal, double *Hw) {
+    const int lane = threadIdx.x & 31;
+    if (lane < E.V || E.V > 32) {
+        const double d = -dot3(center, normal);
+        double Mref[9], inv[9];
+        plane_matrix(E.refKR, E.refKT, normal, d, E.sc, Mref);
+        inv3(Mref, inv);
+        for (int v = lane; v < E.V; v += 32) {
+            const ViewS &vw = E.view[v];
+            double *Hi = Hw + 9 * v;
+            if (vw.isRef) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Hi[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                continue;
+            }
+            double M[9];
+            plane_matrix(vw.KR, vw.KT, normal, d, E.sc, M);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double acc = M[r * 3] * inv[c];
+                    acc += M[r * 3 + 1] * inv[3 + c];
+                    acc += M[r * 3 + 2] * inv[6 + c];
+                    Hi[r * 3 + c] = acc;
+                }
+        }
+    }
+    __syncwarp();
+}
+
+/* The reference walks the window with `for (double x = pt-r; x <= pt+r; ++x)` (patch.cpp:979-980, :347-348):
+ * repeated +1.0 in f64. Lane 0 / lane 1 replay that recurrence so sample positions (and, in the rare case a
+ * rounding step overshoots pt+r, the sample COUNT) are bit-identical. Returns nx | ny<<16 to every lane. */
+__device__ __forceinline__ int warp_window_axes(const double *pt, int radius, int ps, double *xs, double *ys) {
+    const int lane = threadIdx.x & 31;
+    int n = 0;
+    if (lane < 2) {
+        double *dst = lane ? ys : xs;
+        const double hi = pt[lane] + radius;
+        for (double x = pt[lane] - radius; x <= hi && n < ps; x = x + 1.0) dst[n++] = x;
+    }
+    const int nx = __shfl_sync(PMVS_FULL, n, 0), ny = __shfl_sync(PMVS_FULL, n, 1);
+    __syncwarp();
+    return nx | (ny << 16);
+}
+
+#define PMVS_MAGIC_FLOOR 6755399441055744.0 /* 1.5 * 2^52: low word of (x + magic, rounded down) = floor(x) */
+__device__ __forceinline__ double u2d(uint32_t g) { return __hiloint2double(0x43300000, (int)g) - 4503599627370496.0; }
+__device__ __forceinline__ double s2d(int d) {
+    return __hiloint2double(0x43300000, (int)((uint32_t)d ^ 0x80000000u)) - (4503599627370496.0 + 2147483648.0);
+}
+
+/* bilinear sample of one view (patch.cpp:1005-1017) from the quad layout; ix,iy known in-bounds and >= 0 */
+__device__ __forceinline__ double quad_bilinear(const uint32_t *__restrict__ quad, int cols, double ix, double iy) {
+    const double tx = __dadd_rd(ix, PMVS_MAGIC_FLOOR), ty = __dadd_rd(iy, PMVS_MAGIC_FLOOR);
+    const int px = __double2loint(tx), py = __double2loint(ty);
+    const double fx = ix - (tx - PMVS_MAGIC_FLOOR), fy = iy - (ty - PMVS_MAGIC_FLOOR);
+    const uint32_t q = __ldg(quad + (size_t)py * cols + px);
+    const int g00 = q & 0xff, g01 = (q >> 8) & 0xff, g10 = (q >> 16) & 0xff, g11 = q >> 24;
+    const double top = fma(s2d(g01 - g00), fx, u2d(g00));
+    const double bot = fma(s2d(g11 - g10), fx, u2d(g10));
+    return fma(bot - top, fy, top);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PMVS_FULL, v, o);
+    return v;
+}
+
+/* One sample of one view: homography + bounds (CHECK) + bilinear. Returns false when out of bounds. */
+template <bool CHECK>
+__device__ __forceinline__ bool sample_view(const double *__restrict__ H, const ViewS &vw, double x, double y, double &c) {
+    const double w = fma(H[6], x, fma(H[7], y, H[8]));
+    const double nx = fma(H[0], x, fma(H[1], y, H[2]));
+    const double ny = fma(H[3], x, fma(H[4], y, H[5]));
+    double ix, iy;
+    if (CHECK) {
+        ix = nx / w;
+        iy = ny / w;
+        /* patch.cpp:999; NaN coordinates count as out of bounds (the reference would index with (int)NaN) */
+        if (!(ix >= 2.0 && ix < (double)(vw.cols - 3) && iy >= 2.0 && iy < (double)(vw.rows - 3)) || w == 0.0) return false;
+    } else {
+        const double rw = 1.0 / w;
+        ix = nx * rw;
+        iy = ny * rw;
+    }
+    c = quad_bilinear(vw.quad, vw.cols, ix, iy);
+    return true;
+}
+
+/*
+ * The sample loop of getFitness (patch.cpp:979-1042). Lanes stride the window along x; each lane accumulates its
+ * samples in index order, then a fixed xor-tree combines lanes (deterministic). VCAP > 0: the per-view colours of
+ * one sample live in registers (V <= VCAP); VCAP == 0: two passes per sample (V up to 64, no storage).
+ * Returns false when an unmasked sample left a view (only possible with CHECK).
+ */
+template <int VCAP, bool CHECK>
+__device__ __forceinline__ bool fitness_samples(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
+                                                const double *__restrict__ Hw, const double *__restrict__ xs,
+                                                const double *__restrict__ ys, int nx, int ny, double &fitOut, double &swOut) {
+    const int lane = threadIdx.x & 31;
+    const int V = E.V;
+    const double invV = 1.0 / (double)V;
+    const bool useDist = S.cfg.adaptiveDistanceEnable, useDiff = S.cfg.adaptiveDifferenceEnable, useGrad = S.cfg.adaptiveGradientEnable;
+    const double invDiffW = 1.0 / S.cfg.diffWeighting, gradW = S.cfg.gradientWeighting;
+    double fit = 0, sw = 0;
+    bool oob = false;
+    const int total = nx * ny;
+    int i = lane % nx, j = lane / nx;
+    for (int s = lane; s < total; s += 32) {
+        const double x = xs[i], y = ys[j];
+        const int idx = i * ny + j;          /* position of the reference's distance-table iterator (patch.cpp:975,980) */
+        i += 32;
+        while (i >= nx) { i -= nx; ++j; }
+        const int rx = __double2int_rn(x), ry = __double2int_rn(y);                    /* cvRound */
+        const size_t rofs = (size_t)ry * E.refCols + rx;
+        if ((__ldg(E.refQuad + rofs) & 0xff) == 0) continue;                          /* patch.cpp:986 */
+        double mean = 0, sad = 0;
+        if (VCAP > 0) {
+            double c[VCAP > 0 ? VCAP : 1];
+#pragma unroll
+            for (int v = 0; v < VCAP; ++v) {
+                if (v < V) {
+                    if (!sample_view<CHECK>(Hw + 9 * v, E.view[v], x, y, c[v])) oob = true;
+                    if (CHECK && oob) break;
+                    mean += c[v];
+                }
+            }
+            if (CHECK && oob) break;
+            mean *= invV;
+#pragma unroll
+            for (int v = 0; v < VCAP; ++v)
+                if (v < V) sad += fabs(c[v] - mean);
+        } else {
+            for (int v = 0; v < V; ++v) {
+                double c;
+                if (!sample_view<CHECK>(Hw + 9 * v, E.view[v], x, y, c)) oob = true;
+                if (CHECK && oob) break;
+                mean += c;
+            }
+            if (CHECK && oob) break;
+            mean *= invV;
+            for (int v = 0; v < V; ++v) {
+                double c = 0;
+                sample_view<CHECK>(Hw + 9 * v, E.view[v], x, y, c);   /* same arithmetic as pass one */
+                sad += fabs(c - mean);
+            }
+        }
+        const double avgSad = sad * invV;
+        double weight = 1.0;
+        if (useDist) weight *= sDistW[idx];                                           /* patch.cpp:1030-1032 */
+        if (useDiff) weight *= exp(-avgSad * avgSad * invDiffW);                      /* patch.cpp:1033-1035 */
+        if (useGrad) weight *= exp(-1.0 / (__ldg(E.refEdge + rofs) * gradW));         /* patch.cpp:1036-1038 */
+        sw += weight;
+        fit = fma(weight, avgSad, fit);
+    }
+    if (CHECK && __any_sync(PMVS_FULL, oob)) return false;
+    fitOut = warp_sum(fit);
+    swOut = warp_sum(sw);
+    return true;
+}
+
+/*
+ * PAIS::getFitness (patch.cpp:914-1047) for the hypothesis (theta, phi, depth); one warp, result in every lane.
+ * Hypotheses whose window corners all project at least PMVS_EDGE_EPS inside every view take the unchecked loop
+ * (a projective map with w > 0 keeps the window inside the convex hull of its corners); anything else takes the
+ * loop with the reference's per-sample test, so the DBL_MAX sentinel is reproduced exactly.
+ */
+#define PMVS_EDGE_EPS 1e-6
+template <int VCAP>
+__device__ double warp_fitness(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, double theta,
+                               double phi, double depth) {
+    const int lane = threadIdx.x & 31;
+    const int radius = S.cfg.patchRadius, ps = S.cfg.patchSize;
+    double n[3];
+    spherical2Normal(theta, phi, n);                                                  /* :935-936 */
+    if (dot3(n, E.refOptN) > 0) return DBL_MAX;                                       /* :939-941 */
+    double center[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) center[k] = E.ray[k] * depth + E.refC[k];             /* :944 */
+    if (!E.valid) return DBL_MAX;
+    __syncwarp();
+    warp_homographies(E, center, n, W.H);                                             /* :947-948 */
+    double pt[2];
+    project_pt(E.refR, E.refT, E.refFocal, E.refPP, E.sc, center, pt);                /* :951-954 */
+    if (!in_image(pt[0], pt[1], E.refCols, E.refRows)) return DBL_MAX;
+    if (pt[0] - radius < 2 || pt[0] + radius >= E.refCols - 3 || pt[1] - radius < 2 || pt[1] + radius >= E.refRows - 3)
+        return DBL_MAX;                                                               /* :957-962 */
+    const int nxy = warp_window_axes(pt, radius, ps, W.xs, W.ys);
+    const int nx = nxy & 0xffff, ny = nxy >> 16;
+
+    bool inside = true;
+    for (int v = lane; v < E.V; v += 32) {
+        const double *H = W.H + 9 * v;
+        const ViewS &vw = E.view[v];
+        const double loX = 2.0 + PMVS_EDGE_EPS, hiX = (double)(vw.cols - 3) - PMVS_EDGE_EPS;
+        const double loY = 2.0 + PMVS_EDGE_EPS, hiY = (double)(vw.rows - 3) - PMVS_EDGE_EPS;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+            const double x = W.xs[(cidx & 1) ? nx - 1 : 0], y = W.ys[(cidx & 2) ? ny - 1 : 0];
+            const double w = H[6] * x + H[7] * y + H[8];
+            const double ix = (H[0] * x + H[1] * y + H[2]) / w, iy = (H[3] * x + H[4] * y + H[5]) / w;
+            if (!(w > 0.0 && ix >= loX && ix < hiX && iy >= loY && iy < hiY)) inside = false;
+        }
+    }
+    inside = __all_sync(PMVS_FULL, inside);
+    double fit, sw;
+    bool ok;
+    if (inside) ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    __syncwarp();
+    if (!ok) return DBL_MAX;                                                          /* :999-1002 */
+    return fit / sw;                                                                  /* :1046 */
+}
+
+__device__ __forceinline__ double warp_fitness_any(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W,
+                                                   double theta, double phi, double depth) {
+    if (E.V <= 8) return warp_fitness<8>(S, E, sDistW, W, theta, phi, depth);
+    if (E.V <= 16) return warp_fitness<16>(S, E, sDistW, W, theta, phi, depth);
+    return warp_fitness<0>(S, E, sDistW, W, theta, phi, depth);
+}
+
+/* Fill the evaluation context for (refCam, LOD, camIdx[0..V)). Collective over `nthreads` threads with index tid. */
+__device__ __forceinline__ void build_eval_ctx(const DevScene &S, EvalCtx &E, const double *ray, int refCam, int LOD, int V,
+                                               const uint16_t *camIdx, int tid, int nthreads) {
+    if (tid == 0) {
+        bool valid = refCam >= 0 && refCam < S.nCams && LOD >= 0 && LOD < PMVS_MAX_LEVELS && V > 0 && V <= PMVS_MAX_VIEWS;
+        if (valid) {
+            const DevCamera &rc = S.cams[refCam];
+            valid = LOD <= rc.maxLOD;
+            for (int k = 0; k < 3; ++k) {
+                E.ray[k] = ray[k];
+                E.refC[k] = rc.center[k];
+                E.refOptN[k] = rc.optN[k];
+                E.refT[k] = rc.t[k];
+                E.refKT[k] = rc.KT[k];
+            }
+            for (int k = 0; k < 9; ++k) {
+                E.refR[k] = rc.R[k];
+                E.refKR[k] = rc.KR[k];
+            }
+            E.refFocal[0] = rc.focal[0];
+            E.refFocal[1] = rc.focal[1];
+            E.refPP[0] = rc.pp[0];
+            E.refPP[1] = rc.pp[1];
+            if (valid) {
+                E.sc = S.lodScale[LOD];
+                E.refQuad = rc.level[LOD].quad;
+                E.refEdge = rc.level[LOD].edge;
+                E.refCols = rc.level[LOD].cols;
+                E.refRows = rc.level[LOD].rows;
+            }
+        }
+        E.refCam = refCam;
+        E.LOD = LOD;
+        E.V = valid ? V : 0;
+        E.valid = valid ? 1 : 0;
+    }
+    for (int v = tid; v < V && v < PMVS_MAX_VIEWS; v += nthreads) {
+        ViewS &vw = E.view[v];
+        const int ci = camIdx[v];
+        if (ci < S.nCams && LOD >= 0 && LOD < PMVS_MAX_LEVELS) {
+            const DevCamera &cam = S.cams[ci];
+            for (int k = 0; k < 9; ++k) vw.KR[k] = cam.KR[k];
+            for (int k = 0; k < 3; ++k) vw.KT[k] = cam.KT[k];
+            const bool has = LOD <= cam.maxLOD;
+            vw.quad = has ? cam.level[LOD].quad : nullptr;
+            vw.cols = has ? cam.level[LOD].cols : 0;
+            vw.rows = has ? cam.level[LOD].rows : 0;
+            vw.isRef = (ci == refCam);
+        } else {
+            vw.quad = nullptr;
+            vw.cols = vw.rows = 0;
+            vw.isRef = 0;
+        }
+    }
+}
+/* after build_eval_ctx + barrier: a view without the level (cameras of different sizes) invalidates the context —
+ * the reference would index a missing pyramid level there. */
+__device__ __forceinline__ void finish_eval_ctx(EvalCtx &E, int tid) {
+    if (tid == 0 && E.valid)
+        for (int v = 0; v < E.V; ++v)
+            if (E.view[v].quad == nullptr) E.valid = 0;
+}
+
+/* =====================================================================================================
+ * GLN-PSO (pso/psosolver.cpp). State in shared memory; one warp moves / evaluates one particle at a time.
+ * Arithmetic is the reference's expression order without contraction, so given identical fitness values the
+ * swarm is bit-identical to the unmodified reference solver (tests/test_pso_kat.py).
+ * =================================================================================================== */
+struct ParticleS {   /* pso/particle.h:5-28 */
+    double pos[3], vec[3], pBest[3], nBest[3], fitness, pbf, _r0, _r1;
+};
+struct PsoS {
+    double L[3], U[3], inter[3];
+    double iw, gBestFitness;
+    uint64_t key;
+    int P, maxIter, iteration, gBestIdx, localK, converged;
+};
+
+/* lexicographic warp arg-reduction: every lane ends with the winning (key, aux, idx); idx < 0 = no candidate.
+ * `less` true: smaller key wins; false: larger key wins. Ties: smaller aux wins. */
+__device__ __forceinline__ void warp_argbest(double &key, int &aux, int &idx, bool less) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double k2 = __shfl_xor_sync(PMVS_FULL, key, o);
+        const int a2 = __shfl_xor_sync(PMVS_FULL, aux, o);
+        const int i2 = __shfl_xor_sync(PMVS_FULL, idx, o);
+        bool take;
+        if (i2 < 0) take = false;
+        else if (idx < 0) take = true;
+        else take = (less ? (k2 < key) : (k2 > key)) || (k2 == key && a2 < aux);
+        if (take) { key = k2; aux = a2; idx = i2; }
+    }
+}
+
+/* moveParticles for particle p (psosolver.cpp:220-265) incl. getLocalBest (:151-191) and setNearNeighborBest (:193-218) */
+__device__ __forceinline__ void warp_move(PsoS &ps, ParticleS *part, int p, int it, double *wdist) {
+    const int lane = threadIdx.x & 31;
+    const int P = ps.P;
+    ParticleS &me = part[p];
+    const double myB[3] = {me.pBest[0], me.pBest[1], me.pBest[2]};
+    const double myPos[3] = {me.pos[0], me.pos[1], me.pos[2]};
+    const double myFit = me.fitness;
+
+    /* getLocalBest: distances between pBest vectors, self = DBL_MAX */
+    for (int j = lane; j < P; j += 32) {
+        double dist = 0;
+        if (j == p) dist = DBL_MAX;
+        else
+            for (int d = 0; d < 3; ++d) {
+                const double a = myB[d] - part[j].pBest[d];
+                dist += a * a;
+            }
+        wdist[j] = dist;
+    }
+    __syncwarp();
+    /* rank of j in the stable ascending sort; among the first localK pick min pBestFitness, ties -> sorted order */
+    double bk = DBL_MAX;
+    int brank = 0x7fffffff, bj = -1;
+    for (int j = lane; j < P; j += 32) {
+        const double dj = wdist[j];
+        int rank = 0;
+        for (int k = 0; k < P; ++k) {
+            const double dk = wdist[k];
+            rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
+        }
+        if (rank < ps.localK) {
+            const double f = part[j].pbf;
+            if (f < DBL_MAX && (bj < 0 || f < bk || (f == bk && rank < brank))) { bk = f; brank = rank; bj = j; }
+        }
+    }
+    warp_argbest(bk, brank, bj, true);
+    const int lBestIdx = bj < 0 ? p : bj;
+
+    /* setNearNeighborBest: per dimension, first j maximising the fitness-distance ratio */
+    int nIdx[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double fk = 0;
+        int fa = 0x7fffffff, fj = -1;
+        for (int j = lane; j < P; j += 32) {
+            if (j == p) continue;
+            const double FDR = (myFit - part[j].pbf) / fabs(myPos[d] - part[j].pBest[d]);
+            if (FDR > -DBL_MAX && (fj < 0 || FDR > fk)) { fk = FDR; fa = j; fj = j; }
+        }
+        warp_argbest(fk, fa, fj, false);
+        nIdx[d] = fj;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const uint64_t c0 = 6ull * P + 3ull + 4ull * ((uint64_t)it * P + p);
+        const double pVecW = 1.2 * pmvs_random(ps.key, c0);
+        const double gVecW = 1.5 * pmvs_random(ps.key, c0 + 1);
+        const double lVecW = 1.0 * pmvs_random(ps.key, c0 + 2);
+        const double nVecW = 1.0 * pmvs_random(ps.key, c0 + 3);
+        const ParticleS &gb = part[ps.gBestIdx];
+        const ParticleS &lb = part[lBestIdx];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (nIdx[d] >= 0) me.nBest[d] = part[nIdx[d]].pBest[d];
+            const double x = me.pos[d];
+            double v = ps.iw * me.vec[d] + pVecW * (me.pBest[d] - x) + gVecW * (gb.pBest[d] - x) + lVecW * (lb.pBest[d] - x) +
+                       nVecW * (me.nBest[d] - x);
+            double nx = x + v;
+            if (nx > ps.U[d]) nx = ps.U[d];
+            if (nx < ps.L[d]) nx = ps.L[d];
+            me.vec[d] = v;
+            me.pos[d] = nx;
+        }
+    }
+    __syncwarp();
+}
+
+/* updateGbest (psosolver.cpp:137-149), sequential like the reference (<=: the highest index wins ties; NaN never wins) */
+__device__ __forceinline__ void pso_update_gbest(PsoS &ps, const ParticleS *part) {
+    for (int j = 0; j < ps.P; ++j)
+        if (part[j].pbf <= ps.gBestFitness) {
+            ps.gBestFitness = part[j].pbf;
+            ps.gBestIdx = j;
+        }
+}
+
+/*
+ * PsoSolver ctor + setParticle + run(true) (psosolver.cpp:7-43, :94-110, :267-306). CTA-collective.
+ * eval(pos) is warp-collective and returns the fitness in every lane. Returns evaluations spent.
+ */
+template <class Eval>
+__device__ unsigned pso_run(PsoS &ps, ParticleS *part, double *wdist, Eval &eval, const double *init, bool hasInit) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    const int P = ps.P;
+    unsigned evals = 0;
+    for (int i = tid; i < P; i += blockDim.x) {                       /* initParticles :94-110 */
+        ParticleS &q = part[i];
+        for (int d = 0; d < 3; ++d) {
+            const uint64_t c = 2ull * ((uint64_t)d * P + i);
+            q.pos[d] = (ps.inter[d] * pmvs_random(ps.key, c)) + ps.L[d];
+            q.vec[d] = (2.0 * ps.inter[d] * pmvs_random(ps.key, c + 1)) - ps.inter[d];
+            q.pBest[d] = q.pos[d];
+            q.nBest[d] = 0;
+        }
+        q.fitness = 1.7976931348623158e+308;
+        q.pbf = 1.7976931348623158e+308;
+    }
+    __syncthreads();
+    if (tid == 0 && hasInit) {                                        /* setParticle :267-284 */
+        ParticleS &q = part[0];
+        for (int d = 0; d < 3; ++d) {
+            q.pos[d] = init[d];
+            q.pBest[d] = q.pos[d];
+            q.vec[d] = (2.0 * ps.inter[d] * pmvs_random(ps.key, 6ull * P + d)) - ps.inter[d];
+        }
+    }
+    __syncthreads();
+    for (int p = warp; p < P; p += NW) {                              /* initFitness :112-119 */
+        const double f = eval(part[p].pos);
+        if (lane == 0) { part[p].fitness = f; part[p].pbf = f; }
+    }
+    evals += P;
+    __syncthreads();
+    if (tid == 0) {                                                   /* run :288-291 */
+        ps.gBestIdx = 0;
+        ps.gBestFitness = part[0].pbf;
+        ps.iteration = 0;
+        pso_update_gbest(ps, part);
+    }
+    __syncthreads();
+    int it = 0;
+    for (; it < ps.maxIter; ++it) {
+        if (warp == 0) {                                              /* :295, :70-92 (sequential sums) */
+            double index = 0;
+            if (lane == 0) {
+                const double *g = part[ps.gBestIdx].pBest;
+                for (int i = 0; i < P; ++i)
+                    for (int d = 0; d < 3; ++d) index += fabs(part[i].pos[d] - g[d]);
+                index /= (3 * P);
+            } else if (lane == 1) {
+                for (int i = 0; i < P; ++i)
+                    for (int d = 0; d < 3; ++d) index += fabs(part[i].vec[d]);
+                index /= (3 * P);
+            }
+            const double disp = __shfl_sync(PMVS_FULL, index, 0), velo = __shfl_sync(PMVS_FULL, index, 1);
+            if (lane == 0) ps.converged = (disp < 0.01 && velo < 0.01) ? 1 : 0;
+        }
+        __syncthreads();
+        if (ps.converged) break;
+        for (int p = warp; p < P; p += NW) warp_move(ps, part, p, it, wdist);            /* moveParticles */
+        __syncthreads();
+        for (int p = warp; p < P; p += NW) {                                             /* updateFitness :121-135 */
+            const double f = eval(part[p].pos);
+            if (lane == 0) {
+                ParticleS &q = part[p];
+                q.fitness = f;
+                if (f < q.pbf) {
+                    q.pbf = f;
+                    for (int d = 0; d < 3; ++d) q.pBest[d] = q.pos[d];
+                }
+            }
+        }
+        evals += P;
+        __syncthreads();
+        if (tid == 0) {
+            ps.iteration = it;                                                           /* value seen by updateGbest */
+            pso_update_gbest(ps, part);
+            const double niw = ps.iw - 1.0 / ps.maxIter;                                 /* :304 */
+            ps.iw = niw > 0.4 ? niw : 0.4;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) ps.iteration = it;
+    __syncthreads();
+    return evals;
+}
+
+__device__ __forceinline__ void pso_setup(PsoS &ps, const double *L, const double *U, int maxIter, int P, uint64_t key) {
+    for (int d = 0; d < 3; ++d) {
+        ps.L[d] = L[d];
+        ps.U[d] = U[d];
+        ps.inter[d] = U[d] - L[d];
+    }
+    ps.iw = 0.8;
+    ps.gBestFitness = DBL_MAX;
+    ps.key = key;
+    ps.P = P;
+    ps.maxIter = maxIter;
+    ps.iteration = 0;
+    ps.gBestIdx = 0;
+    ps.localK = P < 5 ? P : 5;
+    ps.converged = 0;
+}

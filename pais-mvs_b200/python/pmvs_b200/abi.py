@@ -68,7 +68,7 @@ class PmvsPatchOut(C.Structure):
         ("LOD", C.c_int32), ("refCamIdx", C.c_int32), ("nCam", C.c_int32), ("drop", C.c_int32),
         ("psoRuns", C.c_int32), ("psoIterations", C.c_int32), ("evaluations", C.c_uint32), ("status", C.c_uint32),
         ("camIdx", C.c_uint16 * MAX_VIEWS),
-        ("nImgPoint", C.c_int32), ("_pad", C.c_int32),
+        ("nImgPoint", C.c_int32), ("windowEvaluations", C.c_uint32),
         ("imgPoint", (C.c_double * 2) * MAX_VIEWS),
     ]
 

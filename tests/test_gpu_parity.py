@@ -1,0 +1,273 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs and against the committed golden vectors.
+
+Tolerances. The CUDA path computes in f64. Its sample loop uses fused multiply-adds, a reciprocal-multiply for the
+homography division and CUDA's libm (exp/sincos), so one fitness evaluation agrees with the oracle to ~1e-13
+relative rather than bit-for-bit: FIT_RTOL. The swarm's own arithmetic is bit-exact given equal fitness values
+(test_pso_*), so optimiser decisions only flip when two candidates tie to ~1e-13 — refine() outputs are therefore
+compared at REFINE_RTOL = 1e-4 (BASELINE.json north_star) while the test also REPORTS the worst deviation seen and
+requires the discrete outputs (drop, LOD, reference camera, visibility list, iteration and evaluation counts) to be
+identical."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from pmvs_b200 import abi, scene
+from pmvs_b200.api import PatchRefiner
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FIT_RTOL = 1e-11
+REFINE_RTOL = 1e-4
+
+
+def load_golden_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def assert_fitness_close(got, want, rtol=FIT_RTOL):
+    assert len(got) == len(want)
+    worst = 0.0
+    for i, (g, w) in enumerate(zip(got, want)):
+        if w != w:
+            assert g != g, (i, g, w)
+        elif w == abi.DBL_MAX or g == abi.DBL_MAX:
+            assert g == w, (i, g, w)
+        else:
+            d = abs(g - w) / max(abs(w), 1e-300)
+            worst = max(worst, d)
+            assert d <= rtol, (i, g, w, d)
+    return worst
+
+
+def compare_refine(got, want, rtol=REFINE_RTOL):
+    worst = 0.0
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert (g.drop, g.nCam, list(g.camIdx[:g.nCam]), g.LOD, g.refCamIdx) == \
+               (w.drop, w.nCam, list(w.camIdx[:w.nCam]), w.LOD, w.refCamIdx), i
+        assert (g.psoRuns, g.psoIterations, g.evaluations, g.windowEvaluations, g.status, g.nImgPoint) == \
+               (w.psoRuns, w.psoIterations, w.evaluations, w.windowEvaluations, w.status, w.nImgPoint), i
+        for name in ("center", "normal", "ray", "normalS", "depthRange"):
+            a, b = np.array(getattr(g, name)[:]), np.array(getattr(w, name)[:])
+            d = float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300)) if np.max(np.abs(b)) > 0 else float(np.max(np.abs(a)))
+            worst = max(worst, d)
+            assert d <= rtol, (i, name, a, b)
+        for name in ("fitness", "priority", "correlation", "depth"):
+            a, b = getattr(g, name), getattr(w, name)
+            if b == abi.DBL_MAX or a == abi.DBL_MAX or b != b:
+                assert a == b or (a != a and b != b), (i, name, a, b)
+            else:
+                d = abs(a - b) / max(abs(b), 1e-300)
+                worst = max(worst, d)
+                assert d <= rtol, (i, name, a, b)
+        for k in range(g.nImgPoint):
+            for j in range(2):
+                assert abs(g.imgPoint[k][j] - w.imgPoint[k][j]) <= rtol * max(1.0, abs(w.imgPoint[k][j])), (i, k)
+    return worst
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_pso_bit_exact_against_reference_golden(small_scene):
+    """The swarm alone: GPU == unmodified reference solver (golden) bit for bit, on functions made of exactly
+    rounded operations only."""
+    cfg, sc = small_scene
+    kat = json.load(open(os.path.join(GOLD, "pso_kat.json")))
+    cases = [c for c in kat["cases"] if c["glnpso"] == 1]
+    with PatchRefiner(cfg, sc.records) as pr:
+        res = pr.pso_test([dict(L=c["L"], U=c["U"], init=c["init"], maxIter=c["maxIter"], P=c["P"], fn=c["fn"], key=c["key"])
+                           for c in cases])
+    for c, r in zip(cases, res):
+        assert [v.hex() for v in r["gbest"]] == c["gbest"], c
+        assert r["gbestFitness"].hex() == c["gbestFitness"]
+        assert r["iterations"] == c["iterations"]
+
+
+def test_pso_bit_exact_against_oracle_random(small_scene):
+    cfg, sc = small_scene
+    L = orc.lib()
+    D3 = C.c_double * 3
+    rng = np.random.RandomState(8)
+    probs = []
+    for k in range(64):
+        probs.append(dict(fn=int(rng.choice([0, 1, 3, 4])), P=int(rng.randint(1, 65)), maxIter=int(rng.randint(1, 60)),
+                          L=[-2.0, -1.0, 0.5], U=[1.0, 2.0, 2.5], init=[0.0, 0.5, 1.0] if k % 3 else None,
+                          key=int(rng.randint(1, 1 << 30))))
+    with PatchRefiner(cfg, sc.records) as pr:
+        res = pr.pso_test(probs)
+    for p, r in zip(probs, res):
+        gb, gf, it = D3(), C.c_double(), C.c_int()
+        parts = (C.c_double * (p["P"] * 8))()
+        L.orc_pso_test(p["fn"], D3(*p["L"]), D3(*p["U"]), p["maxIter"], p["P"], D3(*p["init"]) if p["init"] else None, p["key"], 1,
+                       gb, C.byref(gf), C.byref(it), parts)
+        assert list(gb) == r["gbest"] and gf.value == r["gbestFitness"] and it.value == r["iterations"], p
+        want = [list(parts[8 * i:8 * i + 8]) for i in range(p["P"])]
+        assert want == r["particles"], p
+
+
+def test_fitness_golden(small_scene):
+    m = load_golden_module()
+    cfg, sc = m.golden_scene()
+    kat = json.load(open(os.path.join(GOLD, "fitness_kat.json")))
+    assert m.scene_digest(sc) == kat["scene_sha256"]
+    patches = sc.patches(24, seed=77)
+    worst = 0.0
+    for name, c in m.fitness_configs(cfg).items():
+        with PatchRefiner(c, sc.records) as pr:
+            for e in kat["configs"][name]:
+                hy = scene.hypotheses_from_patches(sc, patches, c, lod=e["lod"], seed=5 + e["lod"], per_patch=3, spread=1.0 + e["lod"])
+                worst = max(worst, assert_fitness_close(pr.fitness(hy), [float.fromhex(v) for v in e["fitness"]]))
+    print("fitness golden: worst relative deviation %.3g" % worst)
+
+
+@pytest.mark.parametrize("nviews,radius,weights", [(5, 7, (0, 0, 0)), (5, 15, (1, 1, 0)), (3, 4, (1, 1, 1)), (12, 7, (1, 1, 1)),
+                                                   (20, 5, (1, 1, 0)), (40, 3, (1, 0, 1))])
+def test_fitness_vs_oracle(nviews, radius, weights):
+    """V <= 8 / <= 16 register paths and the V > 16 two-pass path; borders (DBL_MAX), masked pixels, all LODs."""
+    cfg = abi.readme_config()
+    cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = radius, 2 * radius + 1, radius / 3.0, 2
+    cfg.adaptiveDistanceEnable, cfg.adaptiveDifferenceEnable, cfg.adaptiveGradientEnable = weights
+    sc = scene.SynthScene(cfg, nviews=nviews, width=400, height=300, seed=7 + nviews, with_edge=True, tex_size=1024,
+                          background=10, arc_deg=30.0)
+    o = orc.Oracle(cfg, sc.records)
+    patches = sc.patches(60, seed=3, extent=2.4)
+    worst, n_max, n = 0.0, 0, 0
+    with PatchRefiner(cfg, sc.records) as pr:
+        for lod in (0, 1, 2):
+            hy = scene.hypotheses_from_patches(sc, patches, cfg, lod=lod, seed=lod, per_patch=4, spread=2.5)
+            hy[3].theta = math.pi - 0.05
+            want = o.fitness_batch(hy, threads=8)
+            got = pr.fitness(hy)
+            worst = max(worst, assert_fitness_close(got, want))
+            n_max += sum(1 for v in want if v == abi.DBL_MAX)
+            n += len(want)
+    assert 0 < n_max < n
+    print("V=%d r=%d: %d evaluations (%d sentinels), worst relative deviation %.3g" % (nviews, radius, n, n_max, worst))
+
+
+def test_fitness_empty_and_ragged(small_scene):
+    cfg, sc = small_scene
+    with PatchRefiner(cfg, sc.records) as pr:
+        assert pr.fitness((abi.PmvsHypothesis * 0)()) == []
+        hy = scene.hypotheses_from_patches(sc, sc.patches(3, seed=1), cfg, per_patch=1)
+        hy[0].nCam = 1                       # single view: mean == c, avgSad == 0
+        hy[1].nCam = 0                       # no view at all: invalid context
+        hy[2].LOD = 7                        # level the cameras do not have
+        got = pr.fitness(hy)
+        one = (abi.PmvsHypothesis * 1)(hy[0])
+        want = orc.Oracle(cfg, sc.records).fitness_batch(one)
+        assert abs(got[0] - want[0]) < 1e-12
+        assert got[1] == abi.DBL_MAX and got[2] == abi.DBL_MAX     # the reference would index missing data here
+
+
+def test_refine_golden():
+    m = load_golden_module()
+    cfg, sc = m.golden_scene()
+    kat = json.load(open(os.path.join(GOLD, "refine_kat.json")))
+    assert m.scene_digest(sc) == kat["scene_sha256"]
+    worst = 0.0
+    with PatchRefiner(cfg, sc.records, seed=42) as pr:
+        for s in kat["sets"]:
+            ps = sc.patches(s["n"], seed=s["seed"], ptype=s["type"], first_id=s["first_id"])
+            out = pr.refine(ps, flags=abi.F_POST_REMOVE_INVISIBLE)
+            for q, g in zip(out, s["records"]):
+                assert (q.drop, q.nCam, list(q.camIdx[:q.nCam]), q.LOD, q.refCamIdx) == (g["drop"], g["nCam"], g["camIdx"], g["LOD"], g["refCamIdx"])
+                assert (q.psoRuns, q.psoIterations, q.evaluations) == (g["psoRuns"], g["psoIterations"], g["evaluations"])
+                for a, b in zip(list(q.center) + list(q.normal) + [q.fitness, q.correlation],
+                                [float.fromhex(v) for v in g["center"] + g["normal"] + [g["fitness"], g["correlation"]]]):
+                    d = abs(a - b) / max(abs(b), 1e-12)
+                    worst = max(worst, d)
+                    assert d <= REFINE_RTOL, (a, b)
+    print("refine golden: worst relative deviation %.3g" % worst)
+
+
+@pytest.mark.parametrize("case", ["expand_r7", "seed_r7", "wide_arc", "occluded", "gradient_lod", "p5_defaults", "v12"])
+def test_refine_vs_oracle(case):
+    cfg = abi.readme_config()
+    cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = 7, 15, 7 / 3.0, 2
+    kw = dict(nviews=5, width=400, height=300, seed=21, with_edge=True, tex_size=1024)
+    ptype, n, flags, extent = abi.TYPE_EXPAND, 40, abi.F_POST_REMOVE_INVISIBLE, None
+    if case == "seed_r7":
+        ptype, n = abi.TYPE_SEED, 12
+    elif case == "wide_arc":            # cameras beyond the visibility cone: region-ratio / normal tests remove views
+        kw.update(nviews=7, arc_deg=58.0)
+        cfg.minRegionRatio = 0.55
+        flags |= abi.F_EXPAND_VISIBLE
+    elif case == "occluded":
+        kw.update(nviews=6)
+    elif case == "gradient_lod":
+        cfg.adaptiveGradientEnable = 1
+        cfg.textureVariation = 2500.0   # forces LOD > 0 (patch.cpp:546)
+        extent = 2.3                    # border patches: drops and sentinels
+    elif case == "p5_defaults":
+        cfg = abi.default_config()
+        cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = 7, 15, 7 / 3.0, 2
+    elif case == "v12":
+        kw.update(nviews=12, arc_deg=35.0)
+        n = 16
+    sc = scene.SynthScene(cfg, **kw)
+    if case == "occluded":              # one view shows unrelated texture: correlation test removes it (patch.cpp:703)
+        other = scene.SynthScene(cfg, nviews=1, width=400, height=300, seed=999, with_edge=True, tex_size=512)
+        for l in range(len(sc.cams[4].levels)):
+            sc.cams[4].levels[l][0][:] = other.cams[0].levels[l][0]
+    patches = sc.patches(n, seed=5, ptype=ptype, extent=extent)
+    o = orc.Oracle(cfg, sc.records, seed=42, use_ref_pso=orc.ref_lib() is not None)
+    want = o.refine_batch(patches, flags=flags, patch_threads=8)
+    with PatchRefiner(cfg, sc.records, seed=42) as pr:
+        got = pr.refine(patches, flags=flags)
+        again = pr.refine(patches, flags=flags)
+    worst = compare_refine(got, want)
+    assert bytes(got) == bytes(again), "refine_batch is not deterministic"
+    kept = sum(1 for q in want if not q.drop)
+    removed = sum(1 for q, p in zip(want, patches) if not q.drop and q.nCam != p.nCam)
+    print("%s: %d patches, %d kept, %d with views removed, worst relative deviation %.3g" % (case, n, kept, removed, worst))
+    if case in ("wide_arc", "occluded"):
+        assert removed > 0 or kept < n
+
+
+def test_refine_properties_full_size():
+    """BASELINE.json config 2 shape (5 views 1600x1200, r=15, 3 levels, distance+difference weights): properties that
+    need no oracle — batch-order invariance, idempotent re-evaluation, and the recovered plane."""
+    cfg = abi.readme_config()
+    cfg.maxLOD = 2
+    sc = scene.SynthScene(cfg, nviews=5, width=1600, height=1200, seed=1234)
+    n = 296
+    patches = sc.patches(n, seed=5678)
+    with PatchRefiner(cfg, sc.records, seed=42) as pr:
+        out = pr.refine(patches)
+        perm = np.random.RandomState(0).permutation(n)
+        shuffled = (abi.PmvsPatchIn * n)(*[patches[int(i)] for i in perm])
+        out2 = pr.refine(shuffled)
+        for k, i in enumerate(perm):
+            assert bytes(out2[k]) == bytes(out[int(i)])           # keyed by patch id, not by position or CTA
+        hy = (abi.PmvsHypothesis * n)()
+        for i, q in enumerate(out):
+            h = hy[i]
+            h.ray[:] = q.ray[:]
+            h.theta, h.phi, h.depth = q.normalS[0], q.normalS[1], q.depth
+            h.refCamIdx, h.LOD, h.nCam = q.refCamIdx, max(q.LOD, 0), patches[i].nCam
+            h.camIdx[:] = patches[i].camIdx[:]
+        f = pr.fitness(hy)
+    kept = checked = 0
+    for i, q in enumerate(out):
+        if q.drop:
+            continue
+        kept += 1
+        assert abs(q.center[2] - sc.plane_z) < 2e-3 and q.normal[2] > 0.999
+        # same reference camera, LOD and views before and after -> the swarm's best value is reproducible from
+        # its position (the ray is re-normalised after the swarm, hence the small tolerance)
+        nrm0 = np.array(patches[i].normal[:])
+        ref0 = int(np.argmax([float(nrm0 @ (-c.optical_normal)) for c in sc.cams]))
+        if q.nCam == patches[i].nCam and q.refCamIdx == ref0 and q.LOD == 0:
+            checked += 1
+            assert abs(f[i] - q.fitness) <= 1e-9 * max(1.0, q.fitness), (i, f[i], q.fitness)
+    assert kept > 0.9 * n and checked > 0.5 * n
