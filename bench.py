@@ -171,7 +171,8 @@ def run_gpu(args):
     d_out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     gather = torch.empty((world, n, 8), dtype=torch.float64, device=dev) if world > 1 else None
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: kernel, events and NCCL all on it
+    torch.cuda.set_stream(stream)
     flags = abi.F_POST_REMOVE_INVISIBLE
 
     def one_pass(s):

@@ -174,7 +174,7 @@ __device__ inline void patch_to_out(const PatchS &p, PmvsPatchOut &o) {
     }
 }
 
-__global__ void __launch_bounds__(512, 1) refine_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
+__global__ void __launch_bounds__(256, 2) refine_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
                                                         const PmvsPatchIn *__restrict__ in, PmvsPatchOut *__restrict__ out,
                                                         uint32_t flags, int *__restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -368,7 +368,7 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
     /* correlation scratch: one slab per resident CTA */
     const size_t stride = (size_t)ctx->vcap * ctx->cfg.patchSize * ctx->cfg.patchSize;
-    const int ctas = ctx->smCount * 2;
+    const int ctas = ctx->smCount * 4;
     if (stride > ctx->scratchStride || ctas > ctx->scratchCtas || !ctx->dScratch) {
         if (ctx->dScratch) cudaFree(ctx->dScratch);
         ctx->dScratch = nullptr;
@@ -543,14 +543,21 @@ int pmvs_fitness_batch(pmvs_ctx *ctx, int n, const PmvsHypothesis *in, double *o
 }
 
 static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatchOut *d_out, uint32_t flags, cudaStream_t st) {
-    const int maxP = ctx->cfg.particleNum;      /* seeds run 2P particles in rounds over the same warps */
-    const int NW = maxP < 4 ? 4 : (maxP > 16 ? 16 : maxP);
+    /* Warps per CTA: the swarm's P particles (2P for seeds) are evaluated in rounds of NW, one warp per particle.
+     * Small CTAs (4..8 warps) leave room for several patches per SM, so one patch's serial phases (swarm bookkeeping,
+     * visibility) overlap another's evaluations; pick the NW that wastes the fewest warp slots in the last round. */
+    const int P = ctx->cfg.particleNum;
+    int NW = 4, bestWaste = 1 << 30;
+    for (int w = 4; w <= 8; ++w) {
+        const int waste = ((P + w - 1) / w) * w - P;
+        if (waste < bestWaste) { bestWaste = waste; NW = w; }
+    }
     SmemPlan pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, sizeof(CtaS));
     CK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     int perSm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, refine_kernel, NW * 32, pl.total));
     if (perSm < 1) return fail(ctx, PMVS_E_UNSUPPORTED, "refine kernel does not fit on an SM with this configuration");
-    if (perSm > 2) perSm = 2;
+    if (perSm > 16 / NW) perSm = 16 / NW;      /* 16 warps (128 registers each) per SM */
     int grid = ctx->smCount * perSm;
     if (grid > ctx->scratchCtas) grid = ctx->scratchCtas;
     if (grid > n) grid = n;

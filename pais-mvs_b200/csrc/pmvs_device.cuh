@@ -17,6 +17,7 @@
  */
 #pragma once
 #include <cfloat>
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -233,7 +234,7 @@ __device__ __forceinline__ bool sample_view(const double *__restrict__ H, const 
  * Returns false when an unmasked sample left a view (only possible with CHECK).
  */
 template <int VCAP, bool CHECK>
-__device__ __forceinline__ bool fitness_samples(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
+__device__ __noinline__ bool fitness_samples(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
                                                 const double *__restrict__ Hw, const double *__restrict__ xs,
                                                 const double *__restrict__ ys, int nx, int ny, double &fitOut, double &swOut) {
     const int lane = threadIdx.x & 31;
@@ -298,6 +299,154 @@ __device__ __forceinline__ bool fitness_samples(const DevScene &S, const EvalCtx
     return true;
 }
 
+/* 1/w for the unchecked path: MUFU.RCP64H seed (~2^-20) + two Newton steps; w is finite, normal and > 0 there. */
+__device__ __forceinline__ double rcp_fast(double w) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+    double e = fma(-w, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-w, r, 1.0);
+    return fma(r, e, r);
+}
+
+/* explicit shared-memory loads: these helpers run inside non-inlined functions where the compiler only sees
+ * generic pointers; `a` is a 32-bit shared-window address from smem_addr() */
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(unsigned a) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(unsigned a) {
+    unsigned long long v;
+    asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a) {
+    int v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+/* bilinear taps of the unchecked path (patch.cpp:1005-1017) in difference form,
+ *   c = g00 + fx*(g01-g00) + fy*((g10-g00) + fx*(g11-g10-g01+g00)),
+ * tap differences formed in integers, converted by the 2^52+2^31 bias trick (lo word = value + 2^31). */
+#define PMVS_BIAS_S32 (4503599627370496.0 + 2147483648.0)
+__device__ __forceinline__ double quad_bilinear_fast(const uint32_t *__restrict__ quad, int cols, double ix, double iy) {
+    const double tx = __dadd_rd(ix, PMVS_MAGIC_FLOOR), ty = __dadd_rd(iy, PMVS_MAGIC_FLOOR);
+    const int px = __double2loint(tx), py = __double2loint(ty);
+    const double fx = ix - (tx - PMVS_MAGIC_FLOOR), fy = iy - (ty - PMVS_MAGIC_FLOOR);
+    const uint32_t q = __ldg(quad + (py * cols + px));
+    const int g00 = (int)(q & 0xffu), g01 = (int)((q >> 8) & 0xffu), g10 = (int)((q >> 16) & 0xffu), g11 = (int)(q >> 24);
+    const double c00 = __hiloint2double(0x43300000, g00 + (int)0x80000000) - PMVS_BIAS_S32;
+    const double dx = __hiloint2double(0x43300000, g01 - g00 + (int)0x80000000) - PMVS_BIAS_S32;
+    const double dy = __hiloint2double(0x43300000, g10 - g00 + (int)0x80000000) - PMVS_BIAS_S32;
+    const double dxy = __hiloint2double(0x43300000, g11 - g10 - g01 + g00 + (int)0x80000000) - PMVS_BIAS_S32;
+    return fma(fy, fma(fx, dxy, dy), fma(fx, dx, c00));
+}
+
+/*
+ * Unchecked sample loop for exactly VMAX views (compile-time, so every per-view value stays in registers) and windows up
+ * to 32 columns: lane = one window column (several row groups when the window is narrow), so the x-dependent part of
+ * every homography row, A = H0*x+H2, B = H3*x+H5, C = H6*x+H8, is computed once per evaluation and lives in
+ * registers; a sample then costs three fma for the projective coordinates. Two rows are in flight per lane and the
+ * body is branch-free (one basic block) for instruction-level parallelism. The reference view (H = I,
+ * patch.cpp:317-319) goes through the same arithmetic: A = x, B = y-part 0, w = 1 exactly, so its sample is (x, y)
+ * bit-for-bit. Each lane sums its rows in ascending order, then the fixed xor-tree.
+ */
+template <int VMAX>
+struct ColumnViews {
+    double A[VMAX], B[VMAX], C[VMAX];
+};
+
+/* two rows (y0, y1) of one column for all views: avg-SAD of each (patch.cpp:990-1027) */
+template <int VMAX>
+__device__ __forceinline__ void column_rows2(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, double invV, double y0,
+                                             double y1, double &avgSad0, double &avgSad1) {
+    double c0[VMAX], c1[VMAX];
+    double mean0 = 0, mean1 = 0;
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, quad));
+        const int cols = lds_s32(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, cols));
+        const double h1 = lds_f64(hA + 72u * v + 8u), h4 = lds_f64(hA + 72u * v + 32u), h7 = lds_f64(hA + 72u * v + 56u);
+        const double rw0 = rcp_fast(fma(h7, y0, cv.C[v])), rw1 = rcp_fast(fma(h7, y1, cv.C[v]));
+        const double ix0 = fma(h1, y0, cv.A[v]) * rw0, iy0 = fma(h4, y0, cv.B[v]) * rw0;
+        const double ix1 = fma(h1, y1, cv.A[v]) * rw1, iy1 = fma(h4, y1, cv.B[v]) * rw1;
+        c0[v] = quad_bilinear_fast(quad, cols, ix0, iy0);
+        c1[v] = quad_bilinear_fast(quad, cols, ix1, iy1);
+        mean0 += c0[v];
+        mean1 += c1[v];
+    }
+    mean0 *= invV;
+    mean1 *= invV;
+    double sad0 = 0, sad1 = 0;
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        sad0 += fabs(c0[v] - mean0);
+        sad1 += fabs(c1[v] - mean1);
+    }
+    avgSad0 = sad0 * invV;
+    avgSad1 = sad1 * invV;
+}
+
+template <int VMAX>
+__device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
+                                             const double *__restrict__ Hw, const double *__restrict__ xs,
+                                             const double *__restrict__ ys, int nx, int ny, double &fitOut, double &swOut) {
+    const int lane = threadIdx.x & 31;
+    const int G = 32 / nx;                         /* row groups sharing the warp */
+    const int i = lane % nx, g = lane / nx;
+    const bool active = g < G;
+    const unsigned hA = smem_addr(Hw), ysA = smem_addr(ys), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
+    const double x = lds_f64(smem_addr(xs) + 8u * i);
+    const double invV = 1.0 / (double)VMAX;
+    const bool useDist = S.cfg.adaptiveDistanceEnable, useDiff = S.cfg.adaptiveDifferenceEnable, useGrad = S.cfg.adaptiveGradientEnable;
+    const double invDiffW = 1.0 / S.cfg.diffWeighting, gradW = S.cfg.gradientWeighting;
+    ColumnViews<VMAX> cv;
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        const unsigned h = hA + 72u * v;
+        cv.A[v] = fma(lds_f64(h), x, lds_f64(h + 16u));
+        cv.B[v] = fma(lds_f64(h + 24u), x, lds_f64(h + 40u));
+        cv.C[v] = fma(lds_f64(h + 48u), x, lds_f64(h + 64u));
+    }
+    const int rx = __double2int_rn(x);
+    const uint32_t *__restrict__ refQuad = E.refQuad;
+    const double *__restrict__ refEdge = E.refEdge;
+    const int refCols = E.refCols;
+    double fit = 0, sw = 0;
+    const int jEnd = active ? ny : 0;
+    for (int j = g; j < jEnd; j += 2 * G) {
+        const bool two = j + G < jEnd;
+        const int j2 = two ? j + G : j;
+        const double y0 = lds_f64(ysA + 8u * j), y1 = lds_f64(ysA + 8u * j2);
+        const int rofs0 = __double2int_rn(y0) * refCols + rx, rofs1 = __double2int_rn(y1) * refCols + rx;
+        const bool keep0 = (__ldg(refQuad + rofs0) & 0xffu) != 0;                       /* patch.cpp:986 */
+        const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
+        double s0, s1;
+        column_rows2<VMAX>(viewA, hA, cv, invV, y0, y1, s0, s1);
+        double w0 = 1.0, w1 = 1.0;
+        if (useDist) {                                                                    /* patch.cpp:1030-1032 */
+            w0 = lds_f64(distA + 8u * (i * ny + j));
+            w1 = lds_f64(distA + 8u * (i * ny + j2));
+        }
+        if (useDiff) { w0 *= exp(-s0 * s0 * invDiffW); w1 *= exp(-s1 * s1 * invDiffW); }    /* patch.cpp:1033-1035 */
+        if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
+            w0 *= exp(-1.0 / (__ldg(refEdge + rofs0) * gradW));
+            w1 *= exp(-1.0 / (__ldg(refEdge + rofs1) * gradW));
+        }
+        w0 = keep0 ? w0 : 0.0;
+        w1 = keep1 ? w1 : 0.0;
+        sw += w0;
+        fit = fma(w0, s0, fit);
+        sw += w1;
+        fit = fma(w1, s1, fit);
+    }
+    fitOut = warp_sum(fit);
+    swOut = warp_sum(sw);
+}
+
 /*
  * PAIS::getFitness (patch.cpp:914-1047) for the hypothesis (theta, phi, depth); one warp, result in every lane.
  * Hypotheses whose window corners all project at least PMVS_EDGE_EPS inside every view take the unchecked loop
@@ -306,7 +455,7 @@ __device__ __forceinline__ bool fitness_samples(const DevScene &S, const EvalCtx
  */
 #define PMVS_EDGE_EPS 1e-6
 template <int VCAP>
-__device__ double warp_fitness(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, double theta,
+__device__ __noinline__ double warp_fitness(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, double theta,
                                double phi, double depth) {
     const int lane = threadIdx.x & 31;
     const int radius = S.cfg.patchRadius, ps = S.cfg.patchSize;
@@ -344,8 +493,13 @@ __device__ double warp_fitness(const DevScene &S, const EvalCtx &E, const double
     inside = __all_sync(PMVS_FULL, inside);
     double fit, sw;
     bool ok;
-    if (inside) ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
-    else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    if (inside) {
+        ok = true;
+        if (VCAP == 8 && E.V == 5 && nx <= 32 && nx > 0) fitness_columns<5>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+        else if (VCAP == 8 && E.V == 4 && nx <= 32 && nx > 0) fitness_columns<4>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+        else if (VCAP == 8 && E.V == 3 && nx <= 32 && nx > 0) fitness_columns<3>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+        else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     __syncwarp();
     if (!ok) return DBL_MAX;                                                          /* :999-1002 */
     return fit / sw;                                                                  /* :1046 */
@@ -433,7 +587,7 @@ struct PsoS {
     double L[3], U[3], inter[3];
     double iw, gBestFitness;
     uint64_t key;
-    int P, maxIter, iteration, gBestIdx, localK, converged;
+    int P, maxIter, iteration, gBestIdx, localK, converged, drawBase, _pad;
 };
 
 /* lexicographic warp arg-reduction: every lane ends with the winning (key, aux, idx); idx < 0 = no candidate.
@@ -507,7 +661,7 @@ __device__ __forceinline__ void warp_move(PsoS &ps, ParticleS *part, int p, int 
     }
     __syncwarp();
     if (lane == 0) {
-        const uint64_t c0 = 6ull * P + 3ull + 4ull * ((uint64_t)it * P + p);
+        const uint64_t c0 = (uint64_t)ps.drawBase + 4ull * ((uint64_t)it * P + p);
         const double pVecW = 1.2 * pmvs_random(ps.key, c0);
         const double gVecW = 1.5 * pmvs_random(ps.key, c0 + 1);
         const double lVecW = 1.0 * pmvs_random(ps.key, c0 + 2);
@@ -560,6 +714,7 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, double *wdist, Eval &eval
         q.fitness = 1.7976931348623158e+308;
         q.pbf = 1.7976931348623158e+308;
     }
+    if (tid == 0) ps.drawBase = 6 * P + (hasInit ? 3 : 0);           /* draws consumed before the first iteration */
     __syncthreads();
     if (tid == 0 && hasInit) {                                        /* setParticle :267-284 */
         ParticleS &q = part[0];

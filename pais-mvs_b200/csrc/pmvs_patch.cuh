@@ -149,7 +149,7 @@ __device__ inline double fit_ellipse_ratio(const float *px, const float *py, int
 }
 
 /* Patch::getHomographyRegionRatio, patch.cpp:269-288 */
-__device__ inline double region_ratio(int r, const double *pt, const double *H) {
+__device__ __noinline__ double region_ratio(int r, const double *pt, const double *H) {
     const double x[8] = {pt[0] - r, pt[0] - r, pt[0] + r, pt[0] + r, pt[0] - r, pt[0], pt[0] + r, pt[0]};
     const double y[8] = {pt[1] - r, pt[1] + r, pt[1] + r, pt[1] - r, pt[1], pt[1] + r, pt[1], pt[1] - r};
     float fx[8], fy[8];
@@ -414,7 +414,7 @@ __device__ inline void cta_pso_optimization(const DevScene &S, CtaS &c, const do
  * Patch::removeInvisibleCamera (:655-721) with setCorrelationTable (:221-267) and getHomographyPatch (:332-386).
  * Hc: V*9 doubles, xs/ys: window axes, corr: V*V doubles (all shared); hp: this CTA's scratch in HBM (V*ps*ps).
  */
-__device__ inline void cta_remove_invisible(const DevScene &S, CtaS &c, double *Hc, double *xs, double *ys, double *corr,
+__device__ __noinline__ void cta_remove_invisible(const DevScene &S, CtaS &c, double *Hc, double *xs, double *ys, double *corr,
                                             double *hp) {
     PatchS &p = c.p;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;

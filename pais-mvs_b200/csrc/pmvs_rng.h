@@ -9,7 +9,8 @@
  * Draw order of one solver (single-thread order of the reference):
  *   ctor initParticles   psosolver.cpp:100-108   for d<3: for i<P: pos -> ctr 2*(d*P+i), vel -> ctr 2*(d*P+i)+1
  *   setParticle(init)    psosolver.cpp:273-281   vel of particle 0, d = 0..2      -> ctr 6P+d
- *   iteration `it`       psosolver.cpp:232-237   particle i: pVecW,gVecW,lVecW,nVecW -> ctr 6P+3+4*(it*P+i)+{0..3}
+ *   iteration `it`       psosolver.cpp:232-237   particle i: pVecW,gVecW,lVecW,nVecW -> ctr base+4*(it*P+i)+{0..3},
+ *                                                base = 6P+3 after setParticle, 6P without it
  */
 #ifndef PMVS_RNG_H
 #define PMVS_RNG_H

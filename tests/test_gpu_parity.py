@@ -7,7 +7,9 @@ relative rather than bit-for-bit: FIT_RTOL. The swarm's own arithmetic is bit-ex
 (test_pso_*), so optimiser decisions only flip when two candidates tie to ~1e-13 — refine() outputs are therefore
 compared at REFINE_RTOL = 1e-4 (BASELINE.json north_star) while the test also REPORTS the worst deviation seen and
 requires the discrete outputs (drop, LOD, reference camera, visibility list, iteration and evaluation counts) to be
-identical."""
+identical. Measured on B200: expansion patches (30 iterations) agree to ~1e-13; seed patches (60 iterations) reach the
+converged regime where two candidates differ by O(step^2) ~ 1e-13 relative in cost, so a few of them take a different
+late comparison and end ~1e-9 away — still five orders inside the tolerance."""
 import ctypes as C
 import json
 import math
@@ -57,7 +59,11 @@ def compare_refine(got, want, rtol=REFINE_RTOL):
                (w.drop, w.nCam, list(w.camIdx[:w.nCam]), w.LOD, w.refCamIdx), i
         assert (g.psoRuns, g.psoIterations, g.evaluations, g.windowEvaluations, g.status, g.nImgPoint) == \
                (w.psoRuns, w.psoIterations, w.evaluations, w.windowEvaluations, w.status, w.nImgPoint), i
-        for name in ("center", "normal", "ray", "normalS", "depthRange"):
+        # normalS = (theta, phi): phi is a degenerate coordinate at the pole (theta -> 0 leaves the normal unchanged
+        # for any phi), so it is compared as the arc it spans, |dphi|*sin(theta)
+        assert abs(g.normalS[0] - w.normalS[0]) <= rtol, (i, "theta", g.normalS[0], w.normalS[0])
+        assert abs(g.normalS[1] - w.normalS[1]) * abs(math.sin(w.normalS[0])) <= rtol, (i, "phi", g.normalS[1], w.normalS[1])
+        for name in ("center", "normal", "ray", "depthRange"):
             a, b = np.array(getattr(g, name)[:]), np.array(getattr(w, name)[:])
             d = float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300)) if np.max(np.abs(b)) > 0 else float(np.max(np.abs(a)))
             worst = max(worst, d)
