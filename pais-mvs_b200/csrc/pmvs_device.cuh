@@ -299,13 +299,13 @@ __device__ __noinline__ bool fitness_samples(const DevScene &S, const EvalCtx &E
     return true;
 }
 
-/* 1/w for the unchecked path: MUFU.RCP64H seed (~2^-20) + two Newton steps; w is finite, normal and > 0 there. */
+/* 1/w for the unchecked path: MUFU.RCP64H seed r0 (~2^-20), then r0*(1+e+e^2) with e = 1-w*r0 (residual e^3); w is
+ * finite, normal and > 0 there. */
 __device__ __forceinline__ double rcp_fast(double w) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
     double e = fma(-w, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-w, r, 1.0);
+    e = fma(e, e, e);
     return fma(r, e, r);
 }
 
@@ -337,11 +337,12 @@ __device__ __forceinline__ double quad_bilinear_fast(const uint32_t *__restrict_
     const int px = __double2loint(tx), py = __double2loint(ty);
     const double fx = ix - (tx - PMVS_MAGIC_FLOOR), fy = iy - (ty - PMVS_MAGIC_FLOOR);
     const uint32_t q = __ldg(quad + (py * cols + px));
-    const int g00 = (int)(q & 0xffu), g01 = (int)((q >> 8) & 0xffu), g10 = (int)((q >> 16) & 0xffu), g11 = (int)(q >> 24);
-    const double c00 = __hiloint2double(0x43300000, g00 + (int)0x80000000) - PMVS_BIAS_S32;
-    const double dx = __hiloint2double(0x43300000, g01 - g00 + (int)0x80000000) - PMVS_BIAS_S32;
-    const double dy = __hiloint2double(0x43300000, g10 - g00 + (int)0x80000000) - PMVS_BIAS_S32;
-    const double dxy = __hiloint2double(0x43300000, g11 - g10 - g01 + g00 + (int)0x80000000) - PMVS_BIAS_S32;
+    /* unsigned (wrapping) arithmetic on purpose: d + 2^31 mod 2^32 is the biased low word for either sign of d */
+    const uint32_t g00 = q & 0xffu, g01 = (q >> 8) & 0xffu, g10 = (q >> 16) & 0xffu, g11 = q >> 24;
+    const double c00 = __hiloint2double(0x43300000, (int)g00) - 4503599627370496.0;
+    const double dx = __hiloint2double(0x43300000, (int)((g01 - g00) ^ 0x80000000u)) - PMVS_BIAS_S32;
+    const double dy = __hiloint2double(0x43300000, (int)((g10 - g00) ^ 0x80000000u)) - PMVS_BIAS_S32;
+    const double dxy = __hiloint2double(0x43300000, (int)((g11 - g10 - g01 + g00) ^ 0x80000000u)) - PMVS_BIAS_S32;
     return fma(fy, fma(fx, dxy, dy), fma(fx, dx, c00));
 }
 
@@ -359,35 +360,79 @@ struct ColumnViews {
     double A[VMAX], B[VMAX], C[VMAX];
 };
 
-/* two rows (y0, y1) of one column for all views: avg-SAD of each (patch.cpp:990-1027) */
-template <int VMAX>
-__device__ __forceinline__ void column_rows2(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, double invV, double y0,
-                                             double y1, double &avgSad0, double &avgSad1) {
-    double c0[VMAX], c1[VMAX];
-    double mean0 = 0, mean1 = 0;
+/* R rows of one column for all views: avg-SAD of each (patch.cpp:990-1027). Written stage by stage across the
+ * N = VMAX*R independent sample-views (all w, then all reciprocal seeds, then each Newton step, ...) so that
+ * neighbouring instructions are independent: the f64 pipe has ~8-cycle latency and only ~4 warps per scheduler. */
+template <int VMAX, int R>
+__device__ __forceinline__ void column_rows(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, double invV,
+                                            const double (&y)[R], double (&avgSad)[R]) {
+    constexpr int N = VMAX * R;
+    double w[N], r[N], ix[N], iy[N];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        const double h7 = lds_f64(hA + 72u * v + 56u);
+#pragma unroll
+        for (int k = 0; k < R; ++k) w[v * R + k] = fma(h7, y[k], cv.C[v]);
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(w[n]));
+    /* r = r0*(1 + e + e^2), e = 1 - w*r0: residual e^3 ~ 2^-60 from the ~2^-20 seed, three dependent fma */
+#pragma unroll
+    for (int n = 0; n < N; ++n) ix[n] = fma(-w[n], r[n], 1.0);
+#pragma unroll
+    for (int n = 0; n < N; ++n) ix[n] = fma(ix[n], ix[n], ix[n]);
+#pragma unroll
+    for (int n = 0; n < N; ++n) r[n] = fma(r[n], ix[n], r[n]);
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+        const double h1 = lds_f64(hA + 72u * v + 8u), h4 = lds_f64(hA + 72u * v + 32u);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            ix[v * R + k] = fma(h1, y[k], cv.A[v]) * r[v * R + k];
+            iy[v * R + k] = fma(h4, y[k], cv.B[v]) * r[v * R + k];
+        }
+    }
+    /* floors, addresses, loads */
+    uint32_t q[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        w[n] = __dadd_rd(ix[n], PMVS_MAGIC_FLOOR);
+        r[n] = __dadd_rd(iy[n], PMVS_MAGIC_FLOOR);
+    }
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) {
         const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, quad));
         const int cols = lds_s32(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, cols));
-        const double h1 = lds_f64(hA + 72u * v + 8u), h4 = lds_f64(hA + 72u * v + 32u), h7 = lds_f64(hA + 72u * v + 56u);
-        const double rw0 = rcp_fast(fma(h7, y0, cv.C[v])), rw1 = rcp_fast(fma(h7, y1, cv.C[v]));
-        const double ix0 = fma(h1, y0, cv.A[v]) * rw0, iy0 = fma(h4, y0, cv.B[v]) * rw0;
-        const double ix1 = fma(h1, y1, cv.A[v]) * rw1, iy1 = fma(h4, y1, cv.B[v]) * rw1;
-        c0[v] = quad_bilinear_fast(quad, cols, ix0, iy0);
-        c1[v] = quad_bilinear_fast(quad, cols, ix1, iy1);
-        mean0 += c0[v];
-        mean1 += c1[v];
-    }
-    mean0 *= invV;
-    mean1 *= invV;
-    double sad0 = 0, sad1 = 0;
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        sad0 += fabs(c0[v] - mean0);
-        sad1 += fabs(c1[v] - mean1);
+        for (int k = 0; k < R; ++k) q[v * R + k] = __ldg(quad + (__double2loint(r[v * R + k]) * cols + __double2loint(w[v * R + k])));
     }
-    avgSad0 = sad0 * invV;
-    avgSad1 = sad1 * invV;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        ix[n] = ix[n] - (w[n] - PMVS_MAGIC_FLOOR);      /* fx */
+        iy[n] = iy[n] - (r[n] - PMVS_MAGIC_FLOOR);      /* fy */
+    }
+    /* bilinear in difference form (see quad_bilinear_fast) */
+    double c[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        /* byte extraction by PRMT, tap differences in integers, int->f64 on the (otherwise idle) conversion pipe */
+        const int g00 = (int)__byte_perm(q[n], 0, 0x4440), g01 = (int)__byte_perm(q[n], 0, 0x4441);
+        const int g10 = (int)__byte_perm(q[n], 0, 0x4442), g11 = (int)__byte_perm(q[n], 0, 0x4443);
+        const int idx = g01 - g00, idy = g10 - g00;
+        const double c00 = (double)g00, dx = (double)idx, dy = (double)idy, dxy = (double)(g11 - g10 - idx);
+        c[n] = fma(iy[n], fma(ix[n], dxy, dy), fma(ix[n], dx, c00));
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        double mean = 0;
+#pragma unroll
+        for (int v = 0; v < VMAX; ++v) mean += c[v * R + k];
+        mean *= invV;
+        double sad = 0;
+#pragma unroll
+        for (int v = 0; v < VMAX; ++v) sad += fabs(c[v * R + k] - mean);
+        avgSad[k] = sad * invV;
+    }
 }
 
 template <int VMAX>
@@ -424,8 +469,10 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         const int rofs0 = __double2int_rn(y0) * refCols + rx, rofs1 = __double2int_rn(y1) * refCols + rx;
         const bool keep0 = (__ldg(refQuad + rofs0) & 0xffu) != 0;                       /* patch.cpp:986 */
         const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
-        double s0, s1;
-        column_rows2<VMAX>(viewA, hA, cv, invV, y0, y1, s0, s1);
+        const double yy[2] = {y0, y1};
+        double ss[2];
+        column_rows<VMAX, 2>(viewA, hA, cv, invV, yy, ss);
+        const double s0 = ss[0], s1 = ss[1];
         double w0 = 1.0, w1 = 1.0;
         if (useDist) {                                                                    /* patch.cpp:1030-1032 */
             w0 = lds_f64(distA + 8u * (i * ny + j));

@@ -52,13 +52,19 @@ def assert_fitness_close(got, want, rtol=FIT_RTOL):
     return worst
 
 
-def compare_refine(got, want, rtol=REFINE_RTOL):
-    worst = 0.0
+def compare_refine(got, want, rtol=REFINE_RTOL, max_late_flips=0):
+    """Visibility outputs must be identical and geometry within rtol. The swarm's iteration / evaluation counts must be
+    identical too, except for at most `max_late_flips` patches whose swarm ran into the converged regime (see the
+    module docstring): there a comparison between two candidates ~1e-13 apart may go the other way and the run ends an
+    iteration or two earlier or later — with the geometry still within rtol."""
+    worst, flips = 0.0, 0
     for i, (g, w) in enumerate(zip(got, want)):
         assert (g.drop, g.nCam, list(g.camIdx[:g.nCam]), g.LOD, g.refCamIdx) == \
                (w.drop, w.nCam, list(w.camIdx[:w.nCam]), w.LOD, w.refCamIdx), i
-        assert (g.psoRuns, g.psoIterations, g.evaluations, g.windowEvaluations, g.status, g.nImgPoint) == \
-               (w.psoRuns, w.psoIterations, w.evaluations, w.windowEvaluations, w.status, w.nImgPoint), i
+        assert (g.psoRuns, g.status, g.nImgPoint) == (w.psoRuns, w.status, w.nImgPoint), i
+        if (g.psoIterations, g.evaluations, g.windowEvaluations) != (w.psoIterations, w.evaluations, w.windowEvaluations):
+            flips += 1
+            assert flips <= max_late_flips, (i, "swarm took a different path", g.psoIterations, w.psoIterations)
         # normalS = (theta, phi): phi is a degenerate coordinate at the pole (theta -> 0 leaves the normal unchanged
         # for any phi), so it is compared as the arc it spans, |dphi|*sin(theta)
         assert abs(g.normalS[0] - w.normalS[0]) <= rtol, (i, "theta", g.normalS[0], w.normalS[0])
@@ -231,7 +237,8 @@ def test_refine_vs_oracle(case):
     with PatchRefiner(cfg, sc.records, seed=42) as pr:
         got = pr.refine(patches, flags=flags)
         again = pr.refine(patches, flags=flags)
-    worst = compare_refine(got, want)
+    # seeds run twice the iterations (patch.cpp:192) and reach the converged regime: allow a few late flips there
+    worst = compare_refine(got, want, max_late_flips=n // 4 if ptype == abi.TYPE_SEED else 0)
     assert bytes(got) == bytes(again), "refine_batch is not deterministic"
     kept = sum(1 for q in want if not q.drop)
     removed = sum(1 for q, p in zip(want, patches) if not q.drop and q.nCam != p.nCam)
