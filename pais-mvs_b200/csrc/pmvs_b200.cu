@@ -239,7 +239,7 @@ struct TestEval {
 struct PsoTestS {
     PsoS pso;
     ParticleS part[PMVS_MAX_PARTICLES];
-    double dist[16][PMVS_MAX_PARTICLES];
+    MoveS mv;
     double init[3];
 };
 /* one CTA per problem; io = per problem {L3,U3,init3,hasInit,maxIter,P,fn,key(as 2 doubles via bits)} */
@@ -255,7 +255,7 @@ struct PsoTestResult {
 };
 __global__ void __launch_bounds__(512) pso_test_kernel(int n, const PsoTestProblem *__restrict__ prob, PsoTestResult *__restrict__ res) {
     __shared__ PsoTestS s;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const PsoTestProblem &pr = prob[b];
         if (tid == 0) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(512) pso_test_kernel(int n, const PsoTestProbl
         }
         __syncthreads();
         TestEval ev = {pr.fn};
-        pso_run(s.pso, s.part, s.dist[warp], ev, s.init, pr.hasInit != 0);
+        pso_run(s.pso, s.part, s.mv, ev, s.init, pr.hasInit != 0);
         if (tid == 0) {
             PsoTestResult &r = res[b];
             const ParticleS &g = s.part[s.pso.gBestIdx];

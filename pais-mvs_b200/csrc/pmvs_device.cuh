@@ -7,7 +7,7 @@
  *   mvs/camera.cpp:138-160  Camera::project            -> project_pt
  *   mvs/patch.cpp:290-330   Patch::getHomographies     -> warp_homographies
  *   mvs/patch.cpp:914-1047  PAIS::getFitness           -> warp_fitness
- *   pso/psosolver.cpp       PsoSolver (whole file)     -> pso_run / warp_move
+ *   pso/psosolver.cpp       PsoSolver (whole file)     -> pso_run / pso_move_all
  *
  * HBM layout. Every pyramid level of every camera is stored as a "quad" image: one 32-bit word per pixel (x,y)
  * holding the four bilinear taps g(y,x) | g(y,x+1)<<8 | g(y+1,x)<<16 | g(y+1,x+1)<<24 (edge-replicated). The
@@ -469,10 +469,13 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         const int rofs0 = __double2int_rn(y0) * refCols + rx, rofs1 = __double2int_rn(y1) * refCols + rx;
         const bool keep0 = (__ldg(refQuad + rofs0) & 0xffu) != 0;                       /* patch.cpp:986 */
         const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
-        const double yy[2] = {y0, y1};
-        double ss[2];
-        column_rows<VMAX, 2>(viewA, hA, cv, invV, yy, ss);
-        const double s0 = ss[0], s1 = ss[1];
+        /* one row at a time through the staged view loop (five independent chains keep the register budget),
+         * the two rows meet again for the weights so the exp() polynomials overlap */
+        const double ya[1] = {y0}, yb[1] = {y1};
+        double sa[1], sb[1];
+        column_rows<VMAX, 1>(viewA, hA, cv, invV, ya, sa);
+        column_rows<VMAX, 1>(viewA, hA, cv, invV, yb, sb);
+        const double s0 = sa[0], s1 = sb[0];
         double w0 = 1.0, w1 = 1.0;
         if (useDist) {                                                                    /* patch.cpp:1030-1032 */
             w0 = lds_f64(distA + 8u * (i * ny + j));
@@ -623,7 +626,7 @@ __device__ __forceinline__ void finish_eval_ctx(EvalCtx &E, int tid) {
 }
 
 /* =====================================================================================================
- * GLN-PSO (pso/psosolver.cpp). State in shared memory; one warp moves / evaluates one particle at a time.
+ * GLN-PSO (pso/psosolver.cpp). State in shared memory; one warp evaluates one particle at a time, one thread moves one.
  * Arithmetic is the reference's expression order without contraction, so given identical fitness values the
  * swarm is bit-identical to the unmodified reference solver (tests/test_pso_kat.py).
  * =================================================================================================== */
@@ -637,87 +640,93 @@ struct PsoS {
     int P, maxIter, iteration, gBestIdx, localK, converged, drawBase, _pad;
 };
 
-/* lexicographic warp arg-reduction: every lane ends with the winning (key, aux, idx); idx < 0 = no candidate.
- * `less` true: smaller key wins; false: larger key wins. Ties: smaller aux wins. */
-__device__ __forceinline__ void warp_argbest(double &key, int &aux, int &idx, bool less) {
+/*
+ * moveParticles (psosolver.cpp:220-265) incl. getLocalBest (:151-191) and setNearNeighborBest (:193-218), with
+ * thread = particle: every thread scans the other particles j = 0..P-1 in the reference's order, so the selections
+ * (stable k-nearest by pBest distance, first maximum of the fitness-distance ratio) need no reductions and are the
+ * reference's sequential semantics verbatim. The four scans of a particle (local best, FDR in each dimension) are
+ * independent: each kind of scan runs on its own warp, results meet in shared memory.
+ */
+struct MoveS {
+    int lBest[PMVS_MAX_PARTICLES];
+    int nIdx[3][PMVS_MAX_PARTICLES];
+};
+
+__device__ __forceinline__ int pso_local_best(const PsoS &ps, const ParticleS *part, int i) {
+    const int P = ps.P, K = ps.localK;
+    const double b0 = part[i].pBest[0], b1 = part[i].pBest[1], b2 = part[i].pBest[2];
+    /* the localK nearest in stable ascending order of (dist, index): insertion into a sorted register list */
+    double bd[5];
+    int bj[5];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double k2 = __shfl_xor_sync(PMVS_FULL, key, o);
-        const int a2 = __shfl_xor_sync(PMVS_FULL, aux, o);
-        const int i2 = __shfl_xor_sync(PMVS_FULL, idx, o);
-        bool take;
-        if (i2 < 0) take = false;
-        else if (idx < 0) take = true;
-        else take = (less ? (k2 < key) : (k2 > key)) || (k2 == key && a2 < aux);
-        if (take) { key = k2; aux = a2; idx = i2; }
+    for (int k = 0; k < 5; ++k) { bd[k] = DBL_MAX; bj[k] = 0x7fffffff; }
+    for (int j = 0; j < P; ++j) {
+        double d;
+        if (j == i) d = DBL_MAX;
+        else {
+            const double a0 = b0 - part[j].pBest[0], a1 = b1 - part[j].pBest[1], a2 = b2 - part[j].pBest[2];
+            d = a0 * a0;
+            d += a1 * a1;
+            d += a2 * a2;
+        }
+        int id = j;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const bool before = (d < bd[k]) || (d == bd[k] && id < bj[k]);
+            const double td = before ? bd[k] : d;
+            const int tj = before ? bj[k] : id;
+            bd[k] = before ? d : bd[k];
+            bj[k] = before ? id : bj[k];
+            d = td;
+            id = tj;
+        }
     }
+    double minFitness = DBL_MAX;
+    int best = i;                      /* default: the particle's own pBest (:183) */
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < K && bj[k] < P) {
+            const double f = part[bj[k]].pbf;
+            if (f < minFitness) { minFitness = f; best = bj[k]; }
+        }
+    return best;
 }
 
-/* moveParticles for particle p (psosolver.cpp:220-265) incl. getLocalBest (:151-191) and setNearNeighborBest (:193-218) */
-__device__ __forceinline__ void warp_move(PsoS &ps, ParticleS *part, int p, int it, double *wdist) {
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ int pso_near_neighbor(const PsoS &ps, const ParticleS *part, int i, int d) {
+    const double fitness = part[i].fitness, x = part[i].pos[d];
+    double maxFDR = -DBL_MAX;
+    int best = -1;                     /* -1: nBest[d] keeps its previous value (:204-217) */
+    for (int j = 0; j < ps.P; ++j) {
+        if (j == i) continue;
+        const double FDR = (fitness - part[j].pbf) / fabs(x - part[j].pBest[d]);
+        if (FDR > maxFDR) { maxFDR = FDR; best = j; }
+    }
+    return best;
+}
+
+/* CTA-collective: one generation of moves. */
+__device__ __forceinline__ void pso_move_all(PsoS &ps, ParticleS *part, MoveS &mv, int it) {
     const int P = ps.P;
-    ParticleS &me = part[p];
-    const double myB[3] = {me.pBest[0], me.pBest[1], me.pBest[2]};
-    const double myPos[3] = {me.pos[0], me.pos[1], me.pos[2]};
-    const double myFit = me.fitness;
-
-    /* getLocalBest: distances between pBest vectors, self = DBL_MAX */
-    for (int j = lane; j < P; j += 32) {
-        double dist = 0;
-        if (j == p) dist = DBL_MAX;
-        else
-            for (int d = 0; d < 3; ++d) {
-                const double a = myB[d] - part[j].pBest[d];
-                dist += a * a;
-            }
-        wdist[j] = dist;
-    }
-    __syncwarp();
-    /* rank of j in the stable ascending sort; among the first localK pick min pBestFitness, ties -> sorted order */
-    double bk = DBL_MAX;
-    int brank = 0x7fffffff, bj = -1;
-    for (int j = lane; j < P; j += 32) {
-        const double dj = wdist[j];
-        int rank = 0;
-        for (int k = 0; k < P; ++k) {
-            const double dk = wdist[k];
-            rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    for (int kind = warp; kind < 4; kind += NW)          /* one scan kind per warp: no divergence */
+        for (int i = lane; i < P; i += 32) {
+            if (kind == 0) mv.lBest[i] = pso_local_best(ps, part, i);
+            else mv.nIdx[kind - 1][i] = pso_near_neighbor(ps, part, i, kind - 1);
         }
-        if (rank < ps.localK) {
-            const double f = part[j].pbf;
-            if (f < DBL_MAX && (bj < 0 || f < bk || (f == bk && rank < brank))) { bk = f; brank = rank; bj = j; }
-        }
-    }
-    warp_argbest(bk, brank, bj, true);
-    const int lBestIdx = bj < 0 ? p : bj;
-
-    /* setNearNeighborBest: per dimension, first j maximising the fitness-distance ratio */
-    int nIdx[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        double fk = 0;
-        int fa = 0x7fffffff, fj = -1;
-        for (int j = lane; j < P; j += 32) {
-            if (j == p) continue;
-            const double FDR = (myFit - part[j].pbf) / fabs(myPos[d] - part[j].pBest[d]);
-            if (FDR > -DBL_MAX && (fj < 0 || FDR > fk)) { fk = FDR; fa = j; fj = j; }
-        }
-        warp_argbest(fk, fa, fj, false);
-        nIdx[d] = fj;
-    }
-    __syncwarp();
-    if (lane == 0) {
-        const uint64_t c0 = (uint64_t)ps.drawBase + 4ull * ((uint64_t)it * P + p);
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        ParticleS &me = part[i];
+        const uint64_t c0 = (uint64_t)ps.drawBase + 4ull * ((uint64_t)it * P + i);
         const double pVecW = 1.2 * pmvs_random(ps.key, c0);
         const double gVecW = 1.5 * pmvs_random(ps.key, c0 + 1);
         const double lVecW = 1.0 * pmvs_random(ps.key, c0 + 2);
         const double nVecW = 1.0 * pmvs_random(ps.key, c0 + 3);
         const ParticleS &gb = part[ps.gBestIdx];
-        const ParticleS &lb = part[lBestIdx];
+        const ParticleS &lb = part[mv.lBest[i]];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            if (nIdx[d] >= 0) me.nBest[d] = part[nIdx[d]].pBest[d];
+            const int nj = mv.nIdx[d][i];
+            if (nj >= 0) me.nBest[d] = part[nj].pBest[d];
             const double x = me.pos[d];
             double v = ps.iw * me.vec[d] + pVecW * (me.pBest[d] - x) + gVecW * (gb.pBest[d] - x) + lVecW * (lb.pBest[d] - x) +
                        nVecW * (me.nBest[d] - x);
@@ -728,7 +737,7 @@ __device__ __forceinline__ void warp_move(PsoS &ps, ParticleS *part, int p, int 
             me.pos[d] = nx;
         }
     }
-    __syncwarp();
+    __syncthreads();
 }
 
 /* updateGbest (psosolver.cpp:137-149), sequential like the reference (<=: the highest index wins ties; NaN never wins) */
@@ -745,7 +754,7 @@ __device__ __forceinline__ void pso_update_gbest(PsoS &ps, const ParticleS *part
  * eval(pos) is warp-collective and returns the fitness in every lane. Returns evaluations spent.
  */
 template <class Eval>
-__device__ unsigned pso_run(PsoS &ps, ParticleS *part, double *wdist, Eval &eval, const double *init, bool hasInit) {
+__device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, const double *init, bool hasInit) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     const int P = ps.P;
     unsigned evals = 0;
@@ -804,8 +813,7 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, double *wdist, Eval &eval
         }
         __syncthreads();
         if (ps.converged) break;
-        for (int p = warp; p < P; p += NW) warp_move(ps, part, p, it, wdist);            /* moveParticles */
-        __syncthreads();
+        pso_move_all(ps, part, mv, it);                                                  /* moveParticles */
         for (int p = warp; p < P; p += NW) {                                             /* updateFitness :121-135 */
             const double f = eval(part[p].pos);
             if (lane == 0) {

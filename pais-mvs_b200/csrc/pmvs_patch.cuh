@@ -30,6 +30,7 @@ struct CtaS {
     EvalCtx E;
     PsoS pso;
     ParticleS part[PMVS_MAX_PARTICLES];
+    MoveS mv;
     PmvsPatchOut out;
     int nextIdx;
 };
@@ -395,7 +396,7 @@ __device__ inline void cta_pso_optimization(const DevScene &S, CtaS &c, const do
     }
     __syncthreads();
     PatchEval ev = {S, c.E, sDistW, W, &p.windowEvals};
-    const unsigned evals = pso_run(c.pso, c.part, W.dist, ev, sInit, true);
+    const unsigned evals = pso_run(c.pso, c.part, c.mv, ev, sInit, true);
     if (tid == 0) {
         const ParticleS &g = c.part[c.pso.gBestIdx];
         p.fitness = c.pso.gBestFitness;
