@@ -27,7 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "pais-mvs_b200", "python"))
 
 import numpy as np  # noqa: E402
 
-from pmvs_b200 import abi, scene  # noqa: E402
+from pmvs_b200 import abi, scene, shard  # noqa: E402
 
 METRIC = "converged patches/sec (r=15, 5 views 1600x1200)"
 UNIT = "patches/s"
@@ -170,19 +170,24 @@ def run_gpu(args):
     d_in = [torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(dev) for h in host_in]
     d_out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    gather = torch.empty((world, n, 8), dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: kernel, events and NCCL all on it
     torch.cuda.set_stream(stream)
     flags = abi.F_POST_REMOVE_INVISIBLE
 
+    fit_off, drop_off = abi.PmvsPatchOut.fitness.offset, abi.PmvsPatchOut.drop.offset
+
+    def exchange():
+        """Exchange step between expansion rounds: every rank's converged records (centre, normal, fitness, drop)."""
+        rec = d_out.view(n, C.sizeof(abi.PmvsPatchOut))
+        geo = rec[:, :48].contiguous().view(torch.float64)
+        fit = rec[:, fit_off:fit_off + 8].contiguous().view(torch.float64)
+        drp = rec[:, drop_off:drop_off + 4].contiguous().view(torch.int32).double()
+        return shard.allgather_records(torch.cat([geo, fit, drp], dim=1), world * n, rank, world)
+
     def one_pass(s):
         pr.refine_device(n, d_in[s].data_ptr(), d_out.data_ptr(), flags, stream=stream.cuda_stream)
-        if world > 1:      # exchange step: converged centre, normal, fitness, drop of every rank's shard
-            rec = d_out.view(n, C.sizeof(abi.PmvsPatchOut)).contiguous()
-            geo = rec[:, :48].contiguous().view(torch.float64)                       # center, normal
-            fit = rec[:, abi.PmvsPatchOut.fitness.offset:abi.PmvsPatchOut.fitness.offset + 8].contiguous().view(torch.float64)
-            drp = rec[:, abi.PmvsPatchOut.drop.offset:abi.PmvsPatchOut.drop.offset + 4].contiguous().view(torch.int32).double()
-            dist.all_gather_into_tensor(gather.view(world * n, 8), torch.cat([geo, fit, drp], dim=1))
+        if world > 1:
+            exchange()
 
     for s in range(args.warmup):
         one_pass(s)
@@ -201,11 +206,7 @@ def run_gpu(args):
         pr.refine_device(n, d_in[s].data_ptr(), d_out.data_ptr(), flags, stream=stream.cuda_stream)
         e1.record(stream)
         if world > 1:
-            rec = d_out.view(n, C.sizeof(abi.PmvsPatchOut))
-            geo = rec[:, :48].contiguous().view(torch.float64)
-            fit = rec[:, abi.PmvsPatchOut.fitness.offset:abi.PmvsPatchOut.fitness.offset + 8].contiguous().view(torch.float64)
-            drp = rec[:, abi.PmvsPatchOut.drop.offset:abi.PmvsPatchOut.drop.offset + 4].contiguous().view(torch.int32).double()
-            dist.all_gather_into_tensor(gather.view(world * n, 8), torch.cat([geo, fit, drp], dim=1))
+            exchange()
         e2.record(stream)
         e2.synchronize()
         step_ms.append(e0.elapsed_time(e2))

@@ -171,6 +171,23 @@ __device__ __forceinline__ void warp_homographies(const EvalCtx &E, const double
  * rounding step overshoots pt+r, the sample COUNT) are bit-identical. Returns nx | ny<<16 to every lane. */
 __device__ __forceinline__ int warp_window_axes(const double *pt, int radius, int ps, double *xs, double *ys) {
     const int lane = threadIdx.x & 31;
+    /* Fast path: while x0 = pt-r and x0+2r share a binade (and x0 >= 1), every x0+k is exactly representable, so the
+     * recurrence never rounds and x_k == x0 + k bit for bit; the count is #{k < ps : x0+k <= pt+r}. */
+    const double x0 = pt[0] - radius, y0 = pt[1] - radius, xh = pt[0] + radius, yh = pt[1] + radius;
+    const bool exact = x0 >= 1.0 && y0 >= 1.0 && (__double2hiint(x0) >> 20) == (__double2hiint(x0 + 2.0 * radius) >> 20) &&
+                       (__double2hiint(y0) >> 20) == (__double2hiint(y0 + 2.0 * radius) >> 20);
+    if (exact) {
+        int nx = 0, ny = 0;
+        for (int k = lane; k < ps; k += 32) {
+            const double x = x0 + (double)k, y = y0 + (double)k;
+            if (x <= xh) { xs[k] = x; ++nx; }
+            if (y <= yh) { ys[k] = y; ++ny; }
+        }
+        nx = __reduce_add_sync(PMVS_FULL, nx);
+        ny = __reduce_add_sync(PMVS_FULL, ny);
+        __syncwarp();
+        return nx | (ny << 16);
+    }
     int n = 0;
     if (lane < 2) {
         double *dst = lane ? ys : xs;
@@ -360,79 +377,77 @@ struct ColumnViews {
     double A[VMAX], B[VMAX], C[VMAX];
 };
 
-/* R rows of one column for all views: avg-SAD of each (patch.cpp:990-1027). Written stage by stage across the
- * N = VMAX*R independent sample-views (all w, then all reciprocal seeds, then each Newton step, ...) so that
- * neighbouring instructions are independent: the f64 pipe has ~8-cycle latency and only ~4 warps per scheduler. */
-template <int VMAX, int R>
-__device__ __forceinline__ void column_rows(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, double invV,
-                                            const double (&y)[R], double (&avgSad)[R]) {
-    constexpr int N = VMAX * R;
-    double w[N], r[N], ix[N], iy[N];
+/*
+ * One window row of one column, split in two halves so the caller can put independent work between a tap load and
+ * its first use (the L1 round trip is ~40 cycles and there are only ~4 warps per scheduler):
+ *   column_coords: projective coordinates of the V views (staged across views: all w, all reciprocal seeds, each
+ *                  refinement step, ... so neighbouring instructions are independent), floors, and the V tap loads;
+ *   column_blend:  bilinear blend (difference form, see quad_bilinear_fast), cross-view mean and avg-SAD
+ *                  (patch.cpp:990-1027).
+ */
+template <int VMAX>
+struct ColumnTaps {
+    double fx[VMAX], fy[VMAX];
+    uint32_t q[VMAX];
+};
+
+template <int VMAX>
+__device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, double y, ColumnTaps<VMAX> &t) {
+    double w[VMAX], r[VMAX], e[VMAX];
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        const double h7 = lds_f64(hA + 72u * v + 56u);
+    for (int v = 0; v < VMAX; ++v) w[v] = fma(lds_f64(hA + 72u * v + 56u), y, cv.C[v]);
 #pragma unroll
-        for (int k = 0; k < R; ++k) w[v * R + k] = fma(h7, y[k], cv.C[v]);
-    }
-#pragma unroll
-    for (int n = 0; n < N; ++n) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(w[n]));
+    for (int v = 0; v < VMAX; ++v) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[v]) : "d"(w[v]));
     /* r = r0*(1 + e + e^2), e = 1 - w*r0: residual e^3 ~ 2^-60 from the ~2^-20 seed, three dependent fma */
 #pragma unroll
-    for (int n = 0; n < N; ++n) ix[n] = fma(-w[n], r[n], 1.0);
+    for (int v = 0; v < VMAX; ++v) e[v] = fma(-w[v], r[v], 1.0);
 #pragma unroll
-    for (int n = 0; n < N; ++n) ix[n] = fma(ix[n], ix[n], ix[n]);
+    for (int v = 0; v < VMAX; ++v) e[v] = fma(e[v], e[v], e[v]);
 #pragma unroll
-    for (int n = 0; n < N; ++n) r[n] = fma(r[n], ix[n], r[n]);
+    for (int v = 0; v < VMAX; ++v) r[v] = fma(r[v], e[v], r[v]);
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) {
-        const double h1 = lds_f64(hA + 72u * v + 8u), h4 = lds_f64(hA + 72u * v + 32u);
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            ix[v * R + k] = fma(h1, y[k], cv.A[v]) * r[v * R + k];
-            iy[v * R + k] = fma(h4, y[k], cv.B[v]) * r[v * R + k];
-        }
+        t.fx[v] = fma(lds_f64(hA + 72u * v + 8u), y, cv.A[v]) * r[v];      /* ix */
+        t.fy[v] = fma(lds_f64(hA + 72u * v + 32u), y, cv.B[v]) * r[v];     /* iy */
     }
-    /* floors, addresses, loads */
-    uint32_t q[N];
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-        w[n] = __dadd_rd(ix[n], PMVS_MAGIC_FLOOR);
-        r[n] = __dadd_rd(iy[n], PMVS_MAGIC_FLOOR);
+    for (int v = 0; v < VMAX; ++v) {
+        w[v] = __dadd_rd(t.fx[v], PMVS_MAGIC_FLOOR);
+        r[v] = __dadd_rd(t.fy[v], PMVS_MAGIC_FLOOR);
     }
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) {
         const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, quad));
         const int cols = lds_s32(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, cols));
-#pragma unroll
-        for (int k = 0; k < R; ++k) q[v * R + k] = __ldg(quad + (__double2loint(r[v * R + k]) * cols + __double2loint(w[v * R + k])));
+        t.q[v] = __ldg(quad + (__double2loint(r[v]) * cols + __double2loint(w[v])));
     }
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-        ix[n] = ix[n] - (w[n] - PMVS_MAGIC_FLOOR);      /* fx */
-        iy[n] = iy[n] - (r[n] - PMVS_MAGIC_FLOOR);      /* fy */
+    for (int v = 0; v < VMAX; ++v) {
+        t.fx[v] = t.fx[v] - (w[v] - PMVS_MAGIC_FLOOR);
+        t.fy[v] = t.fy[v] - (r[v] - PMVS_MAGIC_FLOOR);
     }
-    /* bilinear in difference form (see quad_bilinear_fast) */
-    double c[N];
+}
+
+template <int VMAX>
+__device__ __forceinline__ double column_blend(const ColumnTaps<VMAX> &t, double invV) {
+    double c[VMAX];
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
+    for (int v = 0; v < VMAX; ++v) {
         /* byte extraction by PRMT, tap differences in integers, int->f64 on the (otherwise idle) conversion pipe */
-        const int g00 = (int)__byte_perm(q[n], 0, 0x4440), g01 = (int)__byte_perm(q[n], 0, 0x4441);
-        const int g10 = (int)__byte_perm(q[n], 0, 0x4442), g11 = (int)__byte_perm(q[n], 0, 0x4443);
+        const int g00 = (int)__byte_perm(t.q[v], 0, 0x4440), g01 = (int)__byte_perm(t.q[v], 0, 0x4441);
+        const int g10 = (int)__byte_perm(t.q[v], 0, 0x4442), g11 = (int)__byte_perm(t.q[v], 0, 0x4443);
         const int idx = g01 - g00, idy = g10 - g00;
         const double c00 = (double)g00, dx = (double)idx, dy = (double)idy, dxy = (double)(g11 - g10 - idx);
-        c[n] = fma(iy[n], fma(ix[n], dxy, dy), fma(ix[n], dx, c00));
+        c[v] = fma(t.fy[v], fma(t.fx[v], dxy, dy), fma(t.fx[v], dx, c00));
     }
+    double mean = 0;
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-        double mean = 0;
+    for (int v = 0; v < VMAX; ++v) mean += c[v];
+    mean *= invV;
+    double sad = 0;
 #pragma unroll
-        for (int v = 0; v < VMAX; ++v) mean += c[v * R + k];
-        mean *= invV;
-        double sad = 0;
-#pragma unroll
-        for (int v = 0; v < VMAX; ++v) sad += fabs(c[v * R + k] - mean);
-        avgSad[k] = sad * invV;
-    }
+    for (int v = 0; v < VMAX; ++v) sad += fabs(c[v] - mean);
+    return sad * invV;
 }
 
 template <int VMAX>
@@ -469,13 +484,12 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         const int rofs0 = __double2int_rn(y0) * refCols + rx, rofs1 = __double2int_rn(y1) * refCols + rx;
         const bool keep0 = (__ldg(refQuad + rofs0) & 0xffu) != 0;                       /* patch.cpp:986 */
         const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
-        /* one row at a time through the staged view loop (five independent chains keep the register budget),
-         * the two rows meet again for the weights so the exp() polynomials overlap */
-        const double ya[1] = {y0}, yb[1] = {y1};
-        double sa[1], sb[1];
-        column_rows<VMAX, 1>(viewA, hA, cv, invV, ya, sa);
-        column_rows<VMAX, 1>(viewA, hA, cv, invV, yb, sb);
-        const double s0 = sa[0], s1 = sb[0];
+        /* both rows' tap loads are in flight before the first one is consumed */
+        ColumnTaps<VMAX> ta, tb;
+        column_coords<VMAX>(viewA, hA, cv, y0, ta);
+        column_coords<VMAX>(viewA, hA, cv, y1, tb);
+        const double s0 = column_blend<VMAX>(ta, invV);
+        const double s1 = column_blend<VMAX>(tb, invV);
         double w0 = 1.0, w1 = 1.0;
         if (useDist) {                                                                    /* patch.cpp:1030-1032 */
             w0 = lds_f64(distA + 8u * (i * ny + j));

@@ -1,0 +1,94 @@
+/*
+ * tmvs — command-line driver: `tmvs -r <file.nvm|.nvm2|.mvs>` is the reference's `TMVS.exe -r` (TMVS/TMVS.cpp:76-122,
+ * :174-203): compiled defaults -> config.txt -> load -> config.txt again -> init.mvs -> seed refinement -> seed.mvs ->
+ * expansion -> exp.mvs / exp.ply / exp.psr, total time printed as "time1". The other reference commands (-f filters,
+ * -v / -a viewer) are outside this repository's scope.
+ *
+ * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
+ * round), --device D, --seed S (run seed of the counter-based PSO RNG), --no-expand, -V (verbose),
+ * --convert IN OUT.mvs (load + write only: needs no GPU).
+ */
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "tmvs.h"
+
+using namespace tmvs;
+
+static bool loadAny(MVS &mvs, const std::string &file) {
+    const size_t dot = file.find_last_of('.');
+    const std::string ext = dot == std::string::npos ? "" : file.substr(dot + 1);
+    if (ext == "nvm") return mvs.loadNVM(file.c_str(), false);
+    if (ext == "nvm2") return mvs.loadNVM(file.c_str(), true);
+    if (ext == "mvs") return mvs.loadMVS(file.c_str());
+    fprintf(stderr, "unknown input type: %s\n", file.c_str());
+    return false;
+}
+
+int main(int argc, char **argv) {
+    std::string mode, input, configFile = "config.txt", outDir, imageDir, convertOut;
+    int roundSize = 256, device = 0;
+    unsigned long long seed = 42;
+    bool expand = true, verbose = false;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if ((a == "-r" || a == "-f" || a == "-v" || a == "-a") && i + 1 < argc) { mode = a; input = argv[++i]; }
+        else if (a == "--convert" && i + 2 < argc) { mode = a; input = argv[++i]; convertOut = argv[++i]; }
+        else if (a == "--config" && i + 1 < argc) configFile = argv[++i];
+        else if (a == "--out-dir" && i + 1 < argc) outDir = argv[++i];
+        else if (a == "--image-dir" && i + 1 < argc) imageDir = argv[++i];
+        else if (a == "--round" && i + 1 < argc) roundSize = atoi(argv[++i]);
+        else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
+        else if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
+        else if (a == "--no-expand") expand = false;
+        else if (a == "-V") verbose = true;
+        else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    if (mode.empty()) {   /* TMVS.cpp:183-197 */
+        printf("usage: tmvs -r <input.nvm|input.nvm2|input.mvs> [--config config.txt] [--out-dir DIR] [--round K] [--device D] [--seed S]\n");
+        return 2;
+    }
+    if (mode == "-f" || mode == "-v" || mode == "-a") {
+        fprintf(stderr, "%s is outside the scope of this build (reconstruction path only)\n", mode.c_str());
+        return 2;
+    }
+    if (!outDir.empty() && outDir[outDir.size() - 1] != '/') outDir += "/";
+    if (!imageDir.empty() && imageDir[imageDir.size() - 1] != '/') imageDir += "/";
+
+    MvsConfig config;
+    setInitConfig(config);                                   /* TMVS.cpp:177 */
+    loadConfig(configFile.c_str(), config);                  /* TMVS.cpp:178 */
+    MVS mvs(config);                                         /* TMVS.cpp:181 */
+    mvs.roundSize = roundSize > 0 ? roundSize : 1;
+    mvs.device = device;
+    mvs.rngSeed = seed;
+    mvs.verbose = verbose;
+    mvs.imageDir = imageDir;
+
+    if (!loadAny(mvs, input)) { fprintf(stderr, "load failed: %s\n", mvs.lastError().c_str()); return 1; }
+    loadConfig(configFile.c_str(), config);                  /* TMVS.cpp:92-93: config.txt wins over the MVS header */
+    mvs.setConfig(config);
+    printf("cameras: %zu patches: %zu\n", mvs.cameras.size(), mvs.patches.size());
+    if (mode == "--convert") return mvs.writeMVS(convertOut.c_str()) ? 0 : 1;
+    if (mvs.patches.empty()) {
+        fprintf(stderr, "no seed points in the input (SIFT seed generation, featuremanager.cpp, is out of scope)\n");
+        return 1;
+    }
+
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    mvs.writeMVS((outDir + "init.mvs").c_str());
+    if (!mvs.refineSeedPatches()) { fprintf(stderr, "seed refinement failed: %s\n", mvs.lastError().c_str()); return 1; }
+    printf("seeds kept: %zu\n", mvs.patches.size());
+    mvs.writeMVS((outDir + "seed.mvs").c_str());
+    if (expand && !mvs.expansionPatches()) { fprintf(stderr, "expansion failed: %s\n", mvs.lastError().c_str()); return 1; }
+    mvs.writeMVS((outDir + "exp.mvs").c_str());
+    mvs.writePLY((outDir + "exp.ply").c_str());
+    mvs.writePSR((outDir + "exp.psr").c_str());
+    const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("patches: %zu refined: %ld gpu_seconds: %f\n", mvs.patches.size(), mvs.refinedCount, mvs.gpuSeconds);
+    printf("time1\t%f\n", total);                            /* TMVS.cpp:118-119 */
+    return 0;
+}

@@ -1,0 +1,130 @@
+/*
+ * tmvs.h — host side of `tmvs -r`: the reference's MVS / Camera / Patch / CellMap / FileLoader / FileWriter roles for the
+ * reconstruction command (TMVS/TMVS.cpp:76-122), in C++ like the reference, with Patch::refine() served by the
+ * B200 library (include/pmvs_b200.h) in batches.
+ *
+ * Kept from the reference: MvsConfig (byte-identical, mvs.h:19-72), the NVM / NVM2 / MVS_V2 / MVS_V3 input formats, the
+ * MVS_V3 / PLY / PSR output formats, config.txt, compiled defaults, seed refinement, cell maps, runtime filtering,
+ * expansion strategies. Changed on purpose: expansion runs in ROUNDS (pop K parents, generate all their candidates,
+ * refine the batch on the GPU, commit serially in parent order) instead of one patch at a time;
+ * images are read as PGM/PPM (no OpenCV here; tools/convert_images.py makes them).
+ */
+#ifndef TMVS_HOST_H
+#define TMVS_HOST_H
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pmvs_b200.h"
+
+namespace tmvs {
+
+typedef PmvsConfig MvsConfig;
+
+enum { EXPANSION_BEST_FIRST = 0, EXPANSION_WORST_FIRST = 1, EXPANSION_BREATH_FIRST = 2, EXPANSION_DEPTH_FIRST = 3 };   /* mvs.h */
+
+struct Level {
+    int cols = 0, rows = 0;
+    std::vector<uint8_t> grey;
+    std::vector<double> edge;
+};
+
+/* Camera, TMVS/mvs/camera.h:15-72 */
+struct Camera {
+    std::string fileName;
+    double focal[2], principal[2], quaternion[4], center[3], radialDistortion;
+    double R[9], t[3], KR[9], KT[3], opticalNormal[3];
+    int cols = 0, rows = 0, maxLOD = 0;
+    std::vector<Level> pyramid;
+    std::vector<uint8_t> rgb;          /* rows*cols*3, R,G,B */
+    bool available = false;
+    bool project(const double X[3], double out[2], int LOD, double lodRatio) const;   /* camera.cpp:138-160 */
+};
+
+/* the AbstractPatch/Patch state the host keeps (abstractpatch.h:21-53) */
+struct Patch {
+    int id = -1, type = PMVS_TYPE_SEED;
+    double center[3] = {0, 0, 0}, normal[3] = {0, 0, 0}, normalS[2] = {0, 0};
+    double fitness = 1.7976931348623157e308, priority = 1.7976931348623157e308, correlation = 0;
+    int LOD = -1, refCamIdx = -1;
+    bool drop = false, expanded = false;
+    uint8_t color[3] = {0, 0, 0};      /* b, g, r like cv::Vec3b */
+    std::vector<int> camIdx;
+    std::vector<double> imgPoint;      /* 2 per entry */
+};
+
+struct CellMap {   /* TMVS/mvs/cellmap.{h,cpp} */
+    int width = 0, height = 0;
+    std::vector<std::vector<int> > cells;
+    void init(int imgW, int imgH, int cellSize);
+    bool inMap(int x, int y) const { return !(x < 0 || y < 0 || x >= width || y >= height); }
+    bool insert(int x, int y, int id);
+    bool drop(int x, int y, int id);
+    const std::vector<int> &cell(int x, int y) const { return cells[(size_t)y * width + x]; }
+};
+
+void setInitConfig(MvsConfig &c);                                   /* TMVS.cpp:26-52 */
+bool loadConfig(const char *fileName, MvsConfig &c);                /* fileloader.cpp:474-565 */
+
+/* image helpers (camera.cpp:51-92) */
+bool readPnm(const std::string &path, int &cols, int &rows, std::vector<uint8_t> &grey, std::vector<uint8_t> &rgb);
+void resizeArea(const std::vector<uint8_t> &src, int cols, int rows, double f, std::vector<uint8_t> &dst, int &dcols, int &drows);
+void edgeImage(const std::vector<uint8_t> &grey, int cols, int rows, std::vector<double> &edge);
+
+class MVS {
+public:
+    MvsConfig cfg;
+    std::vector<Camera> cameras;
+    std::map<int, Patch> patches;
+    std::vector<Patch> deletedPatches;
+    std::vector<CellMap> cellMaps;
+    std::vector<int> queue;
+    int nextId = 0;
+    int roundSize = 256;               /* parents popped per expansion round */
+    int device = 0;
+    uint64_t rngSeed = 42;
+    bool verbose = false;
+    std::string imageDir;              /* prefix for camera image files */
+    long refinedCount = 0;             /* patches sent through refine() */
+    double gpuSeconds = 0;
+
+    explicit MVS(const MvsConfig &c);
+    ~MVS();
+    void setConfig(const MvsConfig &c);                             /* mvs.cpp:42-72 */
+
+    bool loadNVM(const char *fileName, bool nvm2);                  /* fileloader.cpp:251-401 + mvs.cpp:161-169 */
+    bool loadMVS(const char *fileName);                             /* fileloader.cpp:403-472 */
+    bool writeMVS(const char *fileName) const;                      /* filewriter.cpp:71-102 */
+    bool writePLY(const char *fileName) const;                      /* filewriter.cpp:104-139 */
+    bool writePSR(const char *fileName) const;                      /* filewriter.cpp:141-171 */
+
+    bool refineSeedPatches();                                       /* mvs.cpp:196-231 */
+    bool expansionPatches();                                        /* mvs.cpp:233-275, in rounds */
+
+    /* pieces exposed for tests */
+    bool addCamera(Camera &cam, bool loadImage);
+    void reCentering();                                             /* mvs.cpp:135-145, patch.cpp:67-112 */
+    void setNeighborRadius();                                       /* mvs.cpp:147-152 */
+    bool runtimeFiltering(const Patch &p) const;                    /* mvs.cpp:838-898 */
+    void getExpansionPatchCenter(const Camera &cam, const Patch &parent, int cx, int cy, double center[3]) const;   /* mvs.cpp:809-836 */
+    bool skipNeighborCell(const std::vector<int> &cell, const Patch &ref) const;                                    /* mvs.cpp:792-807 */
+    static bool isNeighbor(const Patch &a, const Patch &b, double neighborRadius);                                  /* patch.cpp:6-23 */
+    int getPatchIdFromQueue();                                      /* mvs.cpp:656-788 */
+    const std::string &lastError() const { return err; }
+
+private:
+    pmvs_ctx *ctx = nullptr;
+    std::string err;
+    bool ensureContext();
+    void setCellMaps();                                             /* mvs.cpp:116-133 */
+    void insertPatch(const Patch &p);                               /* mvs.cpp:579-601 */
+    void deletePatch(int id);                                       /* mvs.cpp:607-634 */
+    bool refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::vector<std::vector<int> > *parentCams);
+    void setEstimatedNormal(Patch &p) const;                        /* patch.cpp:390-413 */
+    void patchColor(Patch &p) const;                                /* patch.cpp:648-652 */
+};
+
+}   // namespace tmvs
+#endif

@@ -1,0 +1,967 @@
+/*
+ * tmvs_lib.cpp — host-side reconstruction driver (see tmvs.h). Every function cites the reference lines it stands for
+ * (paths relative to the reference tree). All patch refinement goes through pmvs_refine_batch(); there is no host
+ * implementation of refine() here.
+ */
+#include "tmvs.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace tmvs {
+
+static inline int cvRound(double v) { return (int)std::nearbyint(v); }
+static inline double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * config
+ * ------------------------------------------------------------------------------------------------------- */
+void setInitConfig(MvsConfig &c) {   /* TMVS/TMVS.cpp:26-52 */
+    memset(&c, 0, sizeof(c));
+    c.cellSize = 4;
+    c.patchRadius = 15;
+    c.patchSize = 31;
+    c.reduceNormalRange = 2;
+    c.adaptiveDistanceEnable = 1;
+    c.adaptiveDifferenceEnable = 1;
+    c.adaptiveGradientEnable = 0;
+    c.distWeighting = c.patchRadius / 3.0;
+    c.diffWeighting = 128 * 128;
+    c.gradientWeighting = 10.0;
+    c.minCamNum = 3;
+    c.textureVariation = 36;
+    c.visibleCorrelation = 0.7;
+    c.minCorrelation = 0.7;
+    c.maxFitness = 10.0;
+    c.minLOD = 0;
+    c.maxLOD = 15;
+    c.lodRatio = 0.8;
+    c.maxCellPatchNum = 3;
+    c.neighborRadius = 0.005;
+    c.neighborRadiusScalar = 0.0025;
+    c.minRegionRatio = 0.55;
+    c.depthRangeScalar = 1;
+    c.particleNum = 5;
+    c.maxIteration = 10;
+    c.expansionStrategy = EXPANSION_BEST_FIRST;
+}
+
+bool loadConfig(const char *fileName, MvsConfig &c) {   /* TMVS/io/fileloader.cpp:474-565 */
+    std::ifstream file(fileName);
+    if (!file.is_open()) return false;
+    std::string line;
+    while (std::getline(file, line)) {
+        if (!line.empty() && line[0] == '#') continue;
+        std::istringstream ss(line);
+        std::string key, val;
+        if (!(ss >> key)) continue;
+        if (!(ss >> val)) continue;
+        const double f = atof(val.c_str());
+        const int i = atoi(val.c_str());
+        if (key == "patchRadius") { c.patchRadius = i; c.patchSize = (i << 1) + 1; }
+        else if (key == "reduceNormalRange") c.reduceNormalRange = f;
+        else if (key == "adaptiveDistanceEnable") c.adaptiveDistanceEnable = (uint8_t)(i != 0);
+        else if (key == "adaptiveDifferenceEnable") c.adaptiveDifferenceEnable = (uint8_t)(i != 0);
+        else if (key == "adaptiveGradientEnable") c.adaptiveGradientEnable = (uint8_t)(i != 0);
+        else if (key == "distWeighting") c.distWeighting = f;
+        else if (key == "diffWeighting") c.diffWeighting = f;
+        else if (key == "gradientWeighting") c.gradientWeighting = f;   /* documented in README.md:140-142; the reference parser forgot it */
+        else if (key == "visibleCorrelation") c.visibleCorrelation = f;
+        else if (key == "depthRangeScalar") c.depthRangeScalar = f;
+        else if (key == "particleNum") c.particleNum = i;
+        else if (key == "maxIteration") c.maxIteration = i;
+        else if (key == "cellSize") c.cellSize = i;
+        else if (key == "maxCellPatchNum") c.maxCellPatchNum = i;
+        else if (key == "expansionStrategy") c.expansionStrategy = i;
+        else if (key == "textureVariation") c.textureVariation = f;
+        else if (key == "minLOD") c.minLOD = i;
+        else if (key == "maxLOD") c.maxLOD = i;
+        else if (key == "lodRatio") c.lodRatio = f;
+        else if (key == "minCamNum") c.minCamNum = i;
+        else if (key == "minCorrelation") c.minCorrelation = f;
+        else if (key == "minRegionRatio") c.minRegionRatio = f;
+        else if (key == "maxFitness") c.maxFitness = f;
+        else if (key == "neighborRadiusScalar") c.neighborRadiusScalar = f;
+    }
+    return true;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * images (the reference uses cv::imread / resize / Sobel, camera.cpp:51-92)
+ * ------------------------------------------------------------------------------------------------------- */
+static bool pnmToken(std::istream &in, std::string &tok) {
+    tok.clear();
+    int ch;
+    while ((ch = in.get()) != EOF) {
+        if (ch == '#') { while ((ch = in.get()) != EOF && ch != '\n') {} continue; }
+        if (isspace(ch)) { if (!tok.empty()) return true; continue; }
+        tok.push_back((char)ch);
+    }
+    return !tok.empty();
+}
+
+bool readPnm(const std::string &path, int &cols, int &rows, std::vector<uint8_t> &grey, std::vector<uint8_t> &rgb) {
+    std::ifstream in(path.c_str(), std::ios::binary);
+    if (!in.is_open()) return false;
+    std::string magic, t;
+    if (!pnmToken(in, magic) || (magic != "P5" && magic != "P6")) return false;
+    if (!pnmToken(in, t)) return false;
+    cols = atoi(t.c_str());
+    if (!pnmToken(in, t)) return false;
+    rows = atoi(t.c_str());
+    if (!pnmToken(in, t)) return false;   /* the single whitespace after maxval was consumed by pnmToken */
+    if (atoi(t.c_str()) != 255 || cols <= 0 || rows <= 0) return false;
+    const size_t n = (size_t)cols * rows;
+    grey.resize(n);
+    rgb.resize(n * 3);
+    if (magic == "P5") {
+        in.read((char *)grey.data(), (std::streamsize)n);
+        if ((size_t)in.gcount() != n) return false;
+        for (size_t i = 0; i < n; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = grey[i];
+    } else {
+        in.read((char *)rgb.data(), (std::streamsize)(n * 3));
+        if ((size_t)in.gcount() != n * 3) return false;
+        /* cv::imread(file, 0): fixed-point BT.601 as OpenCV's RGB2GRAY (R*4899 + G*9617 + B*1868 + 8192) >> 14 */
+        for (size_t i = 0; i < n; ++i) grey[i] = (uint8_t)((rgb[3 * i] * 4899 + rgb[3 * i + 1] * 9617 + rgb[3 * i + 2] * 1868 + 8192) >> 14);
+    }
+    return true;
+}
+
+/* cv::resize(..., INTER_AREA) for a non-integer scale < 1 (imgproc resize.cpp, computeResizeAreaTab) */
+static void areaTab(int ssize, int dsize, double scale, std::vector<int> &start, std::vector<std::vector<float> > &w) {
+    start.assign(dsize, 0);
+    w.assign(dsize, std::vector<float>());
+    for (int dx = 0; dx < dsize; ++dx) {
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        const double cell = std::min(scale, ssize - fsx1);
+        int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+        sx2 = std::min(sx2, ssize - 1);
+        sx1 = std::min(sx1, sx2);
+        int first = sx1;
+        if (sx1 - fsx1 > 1e-3) { first = sx1 - 1; w[dx].push_back((float)((sx1 - fsx1) / cell)); }
+        start[dx] = first;
+        for (int sx = sx1; sx < sx2; ++sx) w[dx].push_back((float)(1.0 / cell));
+        if (fsx2 - sx2 > 1e-3) w[dx].push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell));
+    }
+}
+
+void resizeArea(const std::vector<uint8_t> &src, int cols, int rows, double f, std::vector<uint8_t> &dst, int &dcols, int &drows) {
+    dcols = cvRound(cols * f);
+    drows = cvRound(rows * f);
+    const double scale = 1.0 / f;
+    std::vector<int> xs, ys;
+    std::vector<std::vector<float> > wx, wy;
+    areaTab(cols, dcols, scale, xs, wx);
+    areaTab(rows, drows, scale, ys, wy);
+    std::vector<float> tmp((size_t)rows * dcols);
+    for (int y = 0; y < rows; ++y)
+        for (int dx = 0; dx < dcols; ++dx) {
+            float acc = 0;
+            for (size_t k = 0; k < wx[dx].size(); ++k) acc += wx[dx][k] * src[(size_t)y * cols + xs[dx] + (int)k];
+            tmp[(size_t)y * dcols + dx] = acc;
+        }
+    dst.resize((size_t)drows * dcols);
+    for (int dy = 0; dy < drows; ++dy)
+        for (int dx = 0; dx < dcols; ++dx) {
+            float acc = 0;
+            for (size_t k = 0; k < wy[dy].size(); ++k) acc += wy[dy][k] * tmp[(size_t)(ys[dy] + (int)k) * dcols + dx];
+            const int v = cvRound(acc);
+            dst[(size_t)dy * dcols + dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+}
+
+/* Sobel ksize=1 ([-1,0,1], BORDER_REFLECT_101) magnitude, min-max normalised (camera.cpp:71-78) */
+void edgeImage(const std::vector<uint8_t> &g, int cols, int rows, std::vector<double> &edge) {
+    edge.resize((size_t)cols * rows);
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const int xl = x == 0 ? (cols > 1 ? 1 : 0) : x - 1, xr = x == cols - 1 ? (cols > 1 ? cols - 2 : 0) : x + 1;
+            const int yu = y == 0 ? (rows > 1 ? 1 : 0) : y - 1, yd = y == rows - 1 ? (rows > 1 ? rows - 2 : 0) : y + 1;
+            const double gx = (double)g[(size_t)y * cols + xr] - g[(size_t)y * cols + xl];
+            const double gy = (double)g[(size_t)yd * cols + x] - g[(size_t)yu * cols + x];
+            const double e = sqrt(gx * gx + gy * gy);
+            edge[(size_t)y * cols + x] = e;
+            mn = std::min(mn, e);
+            mx = std::max(mx, e);
+        }
+    for (size_t i = 0; i < edge.size(); ++i) edge[i] = (edge[i] - mn) / (mx - mn);
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Camera
+ * ------------------------------------------------------------------------------------------------------- */
+static void quaternionToRotation(const double q[4], double R[9]) {   /* camera.cpp:6-35 */
+    const double qq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double qw = 1, qx = 0, qy = 0, qz = 0;
+    if (qq > 0) { qw = q[0] / qq; qx = q[1] / qq; qy = q[2] / qq; qz = q[3] / qq; }
+    R[0] = qw * qw + qx * qx - qz * qz - qy * qy;
+    R[1] = 2 * qx * qy - 2 * qz * qw;
+    R[2] = 2 * qy * qw + 2 * qz * qx;
+    R[3] = 2 * qx * qy + 2 * qw * qz;
+    R[4] = qy * qy + qw * qw - qz * qz - qx * qx;
+    R[5] = 2 * qz * qy - 2 * qx * qw;
+    R[6] = 2 * qx * qz - 2 * qy * qw;
+    R[7] = 2 * qy * qz + 2 * qw * qx;
+    R[8] = qz * qz + qw * qw - qy * qy - qx * qx;
+}
+
+bool Camera::project(const double X[3], double out[2], int LOD, double lodRatio) const {
+    const double x2 = (R[0] * X[0] + R[1] * X[1] + R[2] * X[2]) + t[0];
+    const double y2 = (R[3] * X[0] + R[4] * X[1] + R[5] * X[2]) + t[1];
+    const double z2 = (R[6] * X[0] + R[7] * X[1] + R[8] * X[2]) + t[2];
+    out[0] = focal[0] * (x2 / z2) + principal[0];
+    out[1] = focal[1] * (y2 / z2) + principal[1];
+    const double sc = pow(lodRatio, LOD);
+    out[0] *= sc;
+    out[1] *= sc;
+    if (LOD > maxLOD || std::isnan(out[0]) || std::isnan(out[1])) return false;   /* camera.h:116-131 */
+    const int lc = pyramid.empty() ? cols : pyramid[LOD].cols, lr = pyramid.empty() ? rows : pyramid[LOD].rows;
+    return !(out[0] < 0 || out[0] >= lc || out[1] < 0 || out[1] >= lr);
+}
+
+/* the Camera ctor, camera.cpp:45-136 */
+bool MVS::addCamera(Camera &cam, bool loadImage) {
+    cam.available = false;
+    if (loadImage) {
+        std::vector<uint8_t> grey;
+        std::string base = imageDir + cam.fileName, stem = base;
+        const size_t dot = base.find_last_of('.'), slash = base.find_last_of("/\\");
+        if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) stem = base.substr(0, dot);
+        const std::string tries[] = {base, stem + ".ppm", stem + ".pgm"};
+        bool ok = false;
+        for (const std::string &p : tries)
+            if (readPnm(p, cam.cols, cam.rows, grey, cam.rgb)) { ok = true; break; }
+        if (!ok) {
+            err = "can't read image " + base + " (PGM/PPM expected; see tools/convert_images.py)";
+            return false;
+        }
+        int m = (int)(log((double)std::max(cam.cols, cam.rows)) / log(1.0 / cfg.lodRatio));   /* camera.cpp:63-64 */
+        cam.maxLOD = std::min(m, (int)cfg.maxLOD);
+        if (cam.maxLOD >= PMVS_MAX_LEVELS) cam.maxLOD = PMVS_MAX_LEVELS - 1;
+        cam.pyramid.resize(cam.maxLOD + 1);
+        cam.pyramid[0].cols = cam.cols;
+        cam.pyramid[0].rows = cam.rows;
+        cam.pyramid[0].grey = grey;
+        for (int i = 1; i <= cam.maxLOD; ++i)
+            resizeArea(grey, cam.cols, cam.rows, pow(cfg.lodRatio, i), cam.pyramid[i].grey, cam.pyramid[i].cols, cam.pyramid[i].rows);
+        if (cfg.adaptiveGradientEnable)      /* the edge pyramid is only read at patch.cpp:1037 */
+            for (int i = 0; i <= cam.maxLOD; ++i) edgeImage(cam.pyramid[i].grey, cam.pyramid[i].cols, cam.pyramid[i].rows, cam.pyramid[i].edge);
+    }
+    if (cam.principal[0] < 0 && cam.principal[1] < 0) {   /* camera.cpp:101-106 */
+        cam.principal[0] = cam.cols >> 1;
+        cam.principal[1] = cam.rows >> 1;
+    }
+    quaternionToRotation(cam.quaternion, cam.R);
+    for (int r = 0; r < 3; ++r) cam.t[r] = -(cam.R[3 * r] * cam.center[0] + cam.R[3 * r + 1] * cam.center[1] + cam.R[3 * r + 2] * cam.center[2]);
+    const double K[9] = {cam.focal[0], 0, cam.principal[0], 0, cam.focal[1], cam.principal[1], 0, 0, 1};
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) cam.KR[3 * r + c] = K[3 * r] * cam.R[c] + K[3 * r + 1] * cam.R[3 + c] + K[3 * r + 2] * cam.R[6 + c];
+        cam.KT[r] = K[3 * r] * cam.t[0] + K[3 * r + 1] * cam.t[1] + K[3 * r + 2] * cam.t[2];
+    }
+    for (int c = 0; c < 3; ++c) cam.opticalNormal[c] = cam.R[6 + c];   /* R^T * (0,0,1), camera.cpp:130-133 */
+    cam.available = true;
+    cameras.push_back(cam);
+    return true;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * CellMap
+ * ------------------------------------------------------------------------------------------------------- */
+void CellMap::init(int imgW, int imgH, int cellSize) {
+    width = (int)std::ceil((double)imgW / (double)cellSize);
+    height = (int)std::ceil((double)imgH / (double)cellSize);
+    cells.assign((size_t)width * height, std::vector<int>());
+}
+bool CellMap::insert(int x, int y, int id) {
+    if (!inMap(x, y)) return false;
+    cells[(size_t)y * width + x].push_back(id);
+    return true;
+}
+bool CellMap::drop(int x, int y, int id) {
+    if (!inMap(x, y)) return false;
+    std::vector<int> &c = cells[(size_t)y * width + x];
+    std::vector<int>::iterator it = std::find(c.begin(), c.end(), id);
+    if (it == c.end()) return false;
+    c.erase(it);
+    return true;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MVS
+ * ------------------------------------------------------------------------------------------------------- */
+MVS::MVS(const MvsConfig &c) {
+    memset(&cfg, 0, sizeof(cfg));
+    setConfig(c);
+}
+MVS::~MVS() {
+    if (ctx) pmvs_destroy(ctx);
+}
+
+void MVS::setConfig(const MvsConfig &c) {   /* mvs.cpp:42-72: neighborRadius is NOT copied (derived at run time) */
+    const double keep = cfg.neighborRadius;
+    cfg = c;
+    cfg.patchSize = (cfg.patchRadius << 1) + 1;
+    cfg.neighborRadius = keep;
+    if (ctx) {
+        if (pmvs_set_config(ctx, &cfg) != PMVS_OK) err = pmvs_last_error(ctx);
+        pmvs_set_neighbor_radius(ctx, cfg.neighborRadius);
+    }
+}
+
+static void normal2Spherical(const double n[3], double s[2]) {   /* utility.h:17-22 */
+    s[0] = acos(n[2]);
+    s[1] = atan2(n[1], n[0]);
+}
+static void spherical2Normal(const double s[2], double n[3]) {   /* utility.h:25-29 */
+    n[0] = sin(s[0]) * cos(s[1]);
+    n[1] = sin(s[0]) * sin(s[1]);
+    n[2] = cos(s[0]);
+}
+
+void MVS::setEstimatedNormal(Patch &p) const {   /* patch.cpp:390-413 */
+    if (p.drop) return;
+    if ((int)p.camIdx.size() < cfg.minCamNum) { p.drop = true; return; }
+    double n[3] = {0, 0, 0};
+    for (size_t i = 0; i < p.camIdx.size(); ++i) {
+        const Camera &cam = cameras[p.camIdx[i]];
+        double d[3] = {cam.center[0] - p.center[0], cam.center[1] - p.center[1], cam.center[2] - p.center[2]};
+        const double inv = 1.0 / sqrt(dot3(d, d));
+        for (int k = 0; k < 3; ++k) n[k] += d[k] * inv;
+    }
+    const double inv = 1.0 / sqrt(dot3(n, n));
+    for (int k = 0; k < 3; ++k) p.normal[k] = n[k] * inv;
+    normal2Spherical(p.normal, p.normalS);
+}
+
+/* symmetric 3x3 pseudo-inverse times b (stands for Mat::inv(DECOMP_SVD)*b at patch.cpp:106) by cyclic Jacobi */
+static void solveSym3(const double A[9], const double b[3], double x[3]) {
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) a[i][j] = A[3 * i + j];
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(a[p][q]) < 1e-300) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s * akq;
+                    a[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s * aqk;
+                    a[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - s * vkq;
+                    v[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    const double lmax = std::max(fabs(a[0][0]), std::max(fabs(a[1][1]), fabs(a[2][2])));
+    x[0] = x[1] = x[2] = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (fabs(a[k][k]) <= lmax * 3 * DBL_EPSILON) continue;
+        const double coef = (v[0][k] * b[0] + v[1][k] * b[1] + v[2][k] * b[2]) / a[k][k];
+        for (int i = 0; i < 3; ++i) x[i] += coef * v[i][k];
+    }
+}
+
+void MVS::reCentering() {   /* mvs.cpp:135-145 -> Patch::reCentering patch.cpp:67-112 */
+    for (std::map<int, Patch>::iterator it = patches.begin(); it != patches.end(); ++it) {
+        Patch &p = it->second;
+        double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+        const int camNum = (int)p.camIdx.size();
+        for (int i = 0; i < camNum && 2 * i + 1 < (int)p.imgPoint.size(); ++i) {
+            const Camera &cam = cameras[p.camIdx[i]];
+            const double q[3] = {(p.imgPoint[2 * i] - cam.principal[0]) / cam.focal[0] - cam.t[0],
+                                 (p.imgPoint[2 * i + 1] - cam.principal[1]) / cam.focal[1] - cam.t[1], 1.0 - cam.t[2]};
+            double n[3];
+            for (int c = 0; c < 3; ++c) n[c] = (cam.R[c] * q[0] + cam.R[3 + c] * q[1] + cam.R[6 + c] * q[2]) - cam.center[c];   /* R^T * (p - t) - C */
+            const double inv = 1.0 / sqrt(dot3(n, n));
+            for (int c = 0; c < 3; ++c) n[c] *= inv;
+            const double *C = cam.center;
+            A[0] += 1 - n[0] * n[0]; A[1] += -n[0] * n[1]; A[2] += -n[0] * n[2];
+            A[3] += -n[0] * n[1]; A[4] += 1 - n[1] * n[1]; A[5] += -n[1] * n[2];
+            A[6] += -n[0] * n[2]; A[7] += -n[1] * n[2]; A[8] += 1 - n[2] * n[2];
+            b[0] += (1 - n[0] * n[0]) * C[0] - n[0] * n[1] * C[1] - n[0] * n[2] * C[2];
+            b[1] += -n[0] * n[1] * C[0] + (1 - n[1] * n[1]) * C[1] - n[1] * n[2] * C[2];
+            b[2] += -n[0] * n[2] * C[0] - n[1] * n[2] * C[1] + (1 - n[2] * n[2]) * C[2];
+        }
+        solveSym3(A, b, p.center);
+        setEstimatedNormal(p);
+    }
+}
+
+void MVS::setNeighborRadius() {   /* mvs.cpp:147-152 + getBoundingVolume :967-990 */
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it)
+        for (int i = 0; i < 3; ++i) {
+            mn[i] = std::min(mn[i], it->second.center[i]);
+            mx[i] = std::max(mx[i], it->second.center[i]);
+        }
+    const double volume = fabs((mx[0] - mn[0]) * (mx[1] - mn[1]) * (mx[2] - mn[2]));
+    cfg.neighborRadius = pow(volume, 1.0 / 3.0) * cfg.neighborRadiusScalar;
+    if (ctx) pmvs_set_neighbor_radius(ctx, cfg.neighborRadius);
+    if (verbose) printf("neighborRadius %f\n", cfg.neighborRadius);
+}
+
+bool MVS::isNeighbor(const Patch &a, const Patch &b, double neighborRadius) {   /* patch.cpp:6-23 */
+    const double d[3] = {a.center[0] - b.center[0], a.center[1] - b.center[1], a.center[2] - b.center[2]};
+    double dist = 0;
+    dist += fabs(dot3(d, a.normal));
+    dist += fabs(dot3(d, b.normal));
+    return dist <= neighborRadius;
+}
+
+bool MVS::runtimeFiltering(const Patch &p) const {   /* mvs.cpp:838-898 */
+    if (p.drop) return false;
+    const int camNum = (int)p.camIdx.size();
+    if (camNum < cfg.minCamNum) return false;
+    if (p.fitness > cfg.maxFitness) return false;
+    if (p.fitness == 0.0) return false;
+    if (p.priority > 10000) return false;
+    if (std::isnan(p.fitness) || std::isnan(p.priority) || std::isnan(p.correlation)) return false;
+    if (p.correlation < cfg.minCorrelation) return false;
+    for (size_t i = 0; i < cameras.size(); ++i) {   /* inside every image and not on background */
+        const Camera &cam = cameras[i];
+        double pt[2];
+        if (!cam.project(p.center, pt, 0, cfg.lodRatio)) return false;
+        if (!cam.pyramid.empty()) {
+            /* cvRound may land on cols/rows (the reference then reads one past the row/image): clamp */
+            const int x = std::min(cvRound(pt[0]), cam.cols - 1), y = std::min(cvRound(pt[1]), cam.rows - 1);
+            if (cam.pyramid[0].grey[(size_t)y * cam.cols + x] == 0) return false;
+        }
+    }
+    int count = 0;
+    for (int i = 0; i < camNum; ++i) {
+        const double *on = cameras[p.camIdx[i]].opticalNormal;
+        const double neg[3] = {-on[0], -on[1], -on[2]};
+        if (dot3(p.normal, neg) > 0) count++;
+    }
+    if (count < cfg.minCamNum) return false;
+    if (cellMaps.empty()) return true;
+    int fullCellCounter = 0;
+    for (int i = 0; i < camNum; ++i) {
+        if (2 * i + 1 >= (int)p.imgPoint.size()) continue;
+        const int cx = (int)(p.imgPoint[2 * i] / cfg.cellSize), cy = (int)(p.imgPoint[2 * i + 1] / cfg.cellSize);
+        const CellMap &m = cellMaps[p.camIdx[i]];
+        if (!m.inMap(cx, cy)) continue;   /* the reference indexes the cell unchecked */
+        const std::vector<int> &cell = m.cell(cx, cy);
+        if (std::find(cell.begin(), cell.end(), p.id) != cell.end()) return true;
+        if ((int)cell.size() >= cfg.maxCellPatchNum) ++fullCellCounter;
+    }
+    if (fullCellCounter >= camNum) return false;
+    return true;
+}
+
+void MVS::getExpansionPatchCenter(const Camera &cam, const Patch &parent, int cx, int cy, double center[3]) const {   /* mvs.cpp:809-836 */
+    const double px = (cx + 0.5) * cfg.cellSize, py = (cy + 0.5) * cfg.cellSize;
+    const double q[3] = {(px - cam.principal[0]) / cam.focal[0] - cam.t[0], (py - cam.principal[1]) / cam.focal[1] - cam.t[1], 1.0 - cam.t[2]};
+    double v12[3], v13[3];
+    for (int c = 0; c < 3; ++c) {
+        const double p3d = cam.R[c] * q[0] + cam.R[3 + c] * q[1] + cam.R[6 + c] * q[2];   /* R^T * (p - t) */
+        v12[c] = p3d - cam.center[c];
+        v13[c] = parent.center[c] - cam.center[c];
+    }
+    const double u = dot3(parent.normal, v13) / dot3(parent.normal, v12);
+    for (int c = 0; c < 3; ++c) center[c] = cam.center[c] + u * v12[c];
+}
+
+bool MVS::skipNeighborCell(const std::vector<int> &cell, const Patch &ref) const {   /* mvs.cpp:792-807 */
+    const int n = (int)cell.size();
+    if (n >= cfg.maxCellPatchNum) return true;
+    for (int k = 0; k < n; ++k) {
+        std::map<int, Patch>::const_iterator it = patches.find(cell[k]);
+        if (it == patches.end()) continue;
+        if (it->second.correlation > cfg.minCorrelation) return true;
+        if (isNeighbor(ref, it->second, cfg.neighborRadius)) return true;
+    }
+    return false;
+}
+
+void MVS::setCellMaps() {   /* mvs.cpp:116-133 (+ initCellMaps :74-88) */
+    cellMaps.assign(cameras.size(), CellMap());
+    for (size_t i = 0; i < cameras.size(); ++i) cellMaps[i].init(cameras[i].cols, cameras[i].rows, cfg.cellSize);
+    for (std::map<int, Patch>::iterator it = patches.begin(); it != patches.end(); ++it) {
+        const Patch &p = it->second;
+        for (size_t i = 0; i < p.camIdx.size() && 2 * i + 1 < p.imgPoint.size(); ++i)
+            cellMaps[p.camIdx[i]].insert((int)(p.imgPoint[2 * i] / cfg.cellSize), (int)(p.imgPoint[2 * i + 1] / cfg.cellSize), p.id);
+    }
+}
+
+void MVS::insertPatch(const Patch &p) {   /* mvs.cpp:579-601 */
+    if (!runtimeFiltering(p)) return;
+    patches.insert(std::pair<int, Patch>(p.id, p));
+    queue.push_back(p.id);
+    for (size_t i = 0; i < p.camIdx.size() && 2 * i + 1 < p.imgPoint.size(); ++i)
+        cellMaps[p.camIdx[i]].insert((int)(p.imgPoint[2 * i] / cfg.cellSize), (int)(p.imgPoint[2 * i + 1] / cfg.cellSize), p.id);
+}
+
+void MVS::deletePatch(int id) {   /* mvs.cpp:607-634 */
+    std::map<int, Patch>::iterator it = patches.find(id);
+    if (it == patches.end()) return;
+    if (!cellMaps.empty()) {
+        const Patch &p = it->second;
+        for (size_t i = 0; i < p.camIdx.size() && 2 * i + 1 < p.imgPoint.size(); ++i)
+            cellMaps[p.camIdx[i]].drop((int)(p.imgPoint[2 * i] / cfg.cellSize), (int)(p.imgPoint[2 * i + 1] / cfg.cellSize), p.id);
+    }
+    deletedPatches.push_back(it->second);
+    patches.erase(it);
+}
+
+int MVS::getPatchIdFromQueue() {   /* mvs.cpp:636-788 */
+    /* entries whose patch is gone or already expanded are erased while scanning, as in the reference */
+    std::vector<int> live;
+    live.reserve(queue.size());
+    for (size_t k = 0; k < queue.size(); ++k) {
+        std::map<int, Patch>::const_iterator it = patches.find(queue[k]);
+        if (it == patches.end() || it->second.expanded) continue;
+        live.push_back(queue[k]);
+    }
+    queue.swap(live);
+    if (queue.empty()) return -1;
+    size_t pick = 0;
+    switch (cfg.expansionStrategy) {
+    default:
+    case EXPANSION_BEST_FIRST: {
+        double top = DBL_MAX;
+        bool found = false;
+        for (size_t k = 0; k < queue.size(); ++k) {
+            const double pr = patches.find(queue[k])->second.priority;
+            if (pr < top) { top = pr; pick = k; found = true; }
+        }
+        if (!found) return -1;      /* every priority is DBL_MAX/NaN: the reference returns -1 and keeps scanning an idle queue */
+        break;
+    }
+    case EXPANSION_WORST_FIRST: {
+        double top = -DBL_MAX;
+        bool found = false;
+        for (size_t k = 0; k < queue.size(); ++k) {
+            const double pr = patches.find(queue[k])->second.priority;
+            if (pr > top) { top = pr; pick = k; found = true; }
+        }
+        if (!found) return -1;
+        break;
+    }
+    case EXPANSION_BREATH_FIRST: pick = 0; break;
+    case EXPANSION_DEPTH_FIRST: pick = queue.size() - 1; break;
+    }
+    const int id = queue[pick];
+    queue.erase(queue.begin() + (long)pick);
+    return id;
+}
+
+/* --- GPU ------------------------------------------------------------------------------------------------ */
+bool MVS::ensureContext() {
+    if (ctx) return true;
+    std::vector<PmvsCamera> recs(cameras.size());
+    for (size_t i = 0; i < cameras.size(); ++i) {
+        const Camera &c = cameras[i];
+        PmvsCamera &r = recs[i];
+        memset(&r, 0, sizeof(r));
+        memcpy(r.focal, c.focal, sizeof(r.focal));
+        memcpy(r.principal, c.principal, sizeof(r.principal));
+        memcpy(r.center, c.center, sizeof(r.center));
+        memcpy(r.R, c.R, sizeof(r.R));
+        memcpy(r.t, c.t, sizeof(r.t));
+        memcpy(r.KR, c.KR, sizeof(r.KR));
+        memcpy(r.KT, c.KT, sizeof(r.KT));
+        memcpy(r.opticalNormal, c.opticalNormal, sizeof(r.opticalNormal));
+        r.maxLOD = c.maxLOD;
+        for (int l = 0; l <= c.maxLOD; ++l) {
+            r.level[l].cols = c.pyramid[l].cols;
+            r.level[l].rows = c.pyramid[l].rows;
+            r.level[l].pitch = c.pyramid[l].cols;
+            r.level[l].grey = c.pyramid[l].grey.data();
+            r.level[l].edge = c.pyramid[l].edge.empty() ? nullptr : c.pyramid[l].edge.data();
+        }
+    }
+    const int rc = pmvs_create(&ctx, &cfg, (int)recs.size(), recs.data(), device, rngSeed);
+    if (rc != PMVS_OK) {
+        err = std::string("pmvs_create: ") + (ctx ? pmvs_last_error(ctx) : "out of memory");
+        if (ctx) pmvs_destroy(ctx);
+        ctx = nullptr;
+        return false;
+    }
+    return true;
+}
+
+void MVS::patchColor(Patch &p) const {   /* patch.cpp:648-652 */
+    if (p.refCamIdx < 0 || p.refCamIdx >= (int)cameras.size()) return;
+    const Camera &rc = cameras[p.refCamIdx];
+    double pt[2];
+    if (rc.rgb.empty() || !rc.project(p.center, pt, 0, cfg.lodRatio)) return;
+    const int x = std::min(cvRound(pt[0]), rc.cols - 1), y = std::min(cvRound(pt[1]), rc.rows - 1);
+    const uint8_t *px = &rc.rgb[((size_t)y * rc.cols + x) * 3];
+    p.color[0] = px[2];
+    p.color[1] = px[1];
+    p.color[2] = px[0];
+}
+
+/* Patch::refine() (+ trailing removeInvisibleCamera) for a batch, on the GPU. parentCams != NULL: expansion patches,
+ * batch[i]->camIdx is replaced by the parent's list and expandVisibleCamera runs on the device. */
+bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::vector<std::vector<int> > *parentCams) {
+    if (batch.empty()) return true;
+    if (!ensureContext()) return false;
+    const int n = (int)batch.size();
+    std::vector<PmvsPatchIn> in(n);
+    std::vector<PmvsPatchOut> out(n);
+    for (int i = 0; i < n; ++i) {
+        const Patch &p = *batch[i];
+        PmvsPatchIn &r = in[i];
+        memset(&r, 0, sizeof(r));
+        memcpy(r.center, p.center, sizeof(r.center));
+        memcpy(r.normal, p.normal, sizeof(r.normal));
+        memcpy(r.normalS, p.normalS, sizeof(r.normalS));
+        r.type = p.type;
+        r.id = p.id;
+        const std::vector<int> &cams = parentCams ? (*parentCams)[i] : p.camIdx;
+        r.nCam = (int)std::min<size_t>(cams.size(), PMVS_MAX_VIEWS);
+        for (int k = 0; k < r.nCam; ++k) r.camIdx[k] = (uint16_t)cams[k];
+    }
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const int rc = pmvs_refine_batch(ctx, n, in.data(), out.data(), flags);
+    gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc != PMVS_OK) { err = std::string("pmvs_refine_batch: ") + pmvs_last_error(ctx); return false; }
+    refinedCount += n;
+    for (int i = 0; i < n; ++i) {
+        Patch &p = *batch[i];
+        const PmvsPatchOut &o = out[i];
+        memcpy(p.center, o.center, sizeof(p.center));
+        memcpy(p.normal, o.normal, sizeof(p.normal));
+        memcpy(p.normalS, o.normalS, sizeof(p.normalS));
+        p.fitness = o.fitness;
+        p.priority = o.priority;
+        p.correlation = o.correlation;
+        p.LOD = o.LOD;
+        p.refCamIdx = o.refCamIdx;
+        p.drop = o.drop != 0;
+        p.camIdx.assign(o.camIdx, o.camIdx + o.nCam);
+        p.imgPoint.resize((size_t)o.nImgPoint * 2);
+        for (int k = 0; k < o.nImgPoint; ++k) { p.imgPoint[2 * k] = o.imgPoint[k][0]; p.imgPoint[2 * k + 1] = o.imgPoint[k][1]; }
+        if (o.nImgPoint > 0) patchColor(p);
+    }
+    return true;
+}
+
+bool MVS::refineSeedPatches() {   /* mvs.cpp:196-231 */
+    if (patches.empty()) { printf("No seed patches\n"); return true; }
+    setNeighborRadius();
+    std::vector<int> few;
+    std::vector<Patch *> batch;
+    for (std::map<int, Patch>::iterator it = patches.begin(); it != patches.end(); ++it) {
+        if ((int)it->second.camIdx.size() < cfg.minCamNum) few.push_back(it->first);
+        else batch.push_back(&it->second);
+    }
+    for (size_t k = 0; k < few.size(); ++k) deletePatch(few[k]);
+    if (!ensureContext()) return false;
+    pmvs_set_neighbor_radius(ctx, cfg.neighborRadius);
+    if (!refineBatch(batch, PMVS_F_POST_REMOVE_INVISIBLE, nullptr)) return false;
+    std::vector<int> bad;
+    for (std::map<int, Patch>::iterator it = patches.begin(); it != patches.end(); ++it)
+        if (!runtimeFiltering(it->second)) bad.push_back(it->first);
+    for (size_t k = 0; k < bad.size(); ++k) deletePatch(bad[k]);
+    setNeighborRadius();
+    return true;
+}
+
+bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
+    setCellMaps();
+    queue.clear();
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) queue.push_back(it->first);
+    setNeighborRadius();
+    if (!ensureContext()) return false;
+    size_t saveTime = 0;
+    struct Cand { int parent, cam, cx, cy; };
+    for (int round = 0;; ++round) {
+        /* 1. pop up to roundSize parents in strategy order */
+        std::vector<int> parents;
+        while ((int)parents.size() < roundSize) {
+            const int id = getPatchIdFromQueue();
+            if (id < 0) break;
+            std::map<int, Patch>::iterator it = patches.find(id);
+            if (it == patches.end()) continue;
+            it->second.expanded = true;
+            if (!runtimeFiltering(it->second)) { deletePatch(id); continue; }   /* mvs.cpp:255-260 */
+            parents.push_back(id);
+        }
+        if (parents.empty()) break;
+        /* 2. candidates of every parent (expandNeighborCell mvs.cpp:529-564) */
+        std::vector<Cand> cands;
+        std::vector<Patch> cpatch;
+        std::vector<std::vector<int> > parentCams;
+        for (size_t k = 0; k < parents.size(); ++k) {
+            const Patch &pth = patches.find(parents[k])->second;
+            for (size_t i = 0; i < pth.camIdx.size() && 2 * i + 1 < pth.imgPoint.size(); ++i) {
+                const int ci = pth.camIdx[i];
+                const CellMap &m = cellMaps[ci];
+                const int cx = (int)(pth.imgPoint[2 * i] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * i + 1] / cfg.cellSize);
+                const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
+                for (int j = 0; j < 4; ++j) {
+                    if (!m.inMap(nx[j], ny[j])) continue;
+                    if (skipNeighborCell(m.cell(nx[j], ny[j]), pth)) continue;
+                    Patch e;                                   /* Patch(center, parent), patch.cpp:36-43 */
+                    e.type = PMVS_TYPE_EXPAND;
+                    e.id = nextId++;
+                    getExpansionPatchCenter(cameras[ci], pth, nx[j], ny[j], e.center);
+                    memcpy(e.normal, pth.normal, sizeof(e.normal));
+                    normal2Spherical(e.normal, e.normalS);
+                    const Cand c = {parents[k], ci, nx[j], ny[j]};
+                    cands.push_back(c);
+                    cpatch.push_back(e);
+                    parentCams.push_back(pth.camIdx);
+                }
+            }
+        }
+        /* 3. refine the whole round on the GPU (expandVisibleCamera + refine + removeInvisibleCamera, mvs.cpp:572-574) */
+        std::vector<Patch *> batch(cpatch.size());
+        for (size_t k = 0; k < cpatch.size(); ++k) batch[k] = &cpatch[k];
+        if (!refineBatch(batch, PMVS_F_EXPAND_VISIBLE | PMVS_F_POST_REMOVE_INVISIBLE, &parentCams)) return false;
+        /* 4. commit serially in parent order; a cell another candidate of this round filled in the meantime is
+         *    re-checked exactly like the reference would have seen it (skipNeighborCell + insertPatch) */
+        size_t accepted = 0;
+        for (size_t k = 0; k < cands.size(); ++k) {
+            std::map<int, Patch>::const_iterator pit = patches.find(cands[k].parent);
+            if (pit == patches.end()) continue;
+            if (skipNeighborCell(cellMaps[cands[k].cam].cell(cands[k].cx, cands[k].cy), pit->second)) continue;
+            const size_t before = patches.size();
+            insertPatch(cpatch[k]);
+            accepted += patches.size() - before;
+        }
+        if (verbose)
+            printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), cands.size(), accepted,
+                   patches.size(), queue.size());
+        if (patches.size() / 500 > saveTime) {   /* mvs.cpp:265-268 */
+            saveTime = patches.size() / 500;
+            writeMVS("auto_save.mvs");
+        }
+    }
+    setNeighborRadius();
+    return true;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * loaders / writers
+ * ------------------------------------------------------------------------------------------------------- */
+static std::string dirOf(const char *fileName) {   /* FileLoader::getDir, fileloader.cpp:9-13 */
+    const std::string s(fileName);
+    const size_t found = s.find_last_of("/\\");
+    return found == std::string::npos ? std::string() : s.substr(0, found + 1);
+}
+
+bool MVS::loadNVM(const char *fileName, bool nvm2) {   /* fileloader.cpp:251-325 (NVM), :327-401 (NVM2) */
+    cameras.clear();
+    patches.clear();
+    std::ifstream file(fileName);
+    if (!file.is_open()) { err = std::string("can't open NVM file ") + fileName; return false; }
+    if (imageDir.empty()) imageDir = dirOf(fileName);
+    std::string line;
+    int stage = 0;   /* 0: header, 1: camera count, 2: point count */
+    while (std::getline(file, line)) {
+        std::istringstream ss(line);
+        std::string tok;
+        if (!(ss >> tok)) continue;
+        if (stage == 0) {
+            if (tok == "NVM_V3") stage = 1;
+            continue;
+        }
+        if (stage == 1) {
+            const int num = atoi(tok.c_str());
+            for (int i = 0; i < num; ++i) {
+                if (!std::getline(file, line)) { err = "NVM: truncated camera list"; return false; }
+                std::istringstream cs(line);
+                Camera cam;
+                cam.principal[0] = cam.principal[1] = -1;
+                cam.radialDistortion = 0;
+                if (!(cs >> cam.fileName >> cam.focal[0])) { err = "NVM: bad camera line"; return false; }
+                if (nvm2) cs >> cam.focal[1] >> cam.principal[0] >> cam.principal[1];
+                else cam.focal[1] = cam.focal[0];
+                cs >> cam.quaternion[0] >> cam.quaternion[1] >> cam.quaternion[2] >> cam.quaternion[3];
+                cs >> cam.center[0] >> cam.center[1] >> cam.center[2];
+                if (!nvm2) cs >> cam.radialDistortion;
+                if (cs.fail()) { err = "NVM: bad camera line"; return false; }
+                if (!addCamera(cam, true)) return false;
+            }
+            stage = 2;
+            continue;
+        }
+        if (stage == 2) {
+            const int num = atoi(tok.c_str());
+            for (int i = 0; i < num; ++i) {   /* loadNvmPatch, fileloader.cpp:112-165 */
+                if (!std::getline(file, line)) { err = "NVM: truncated point list"; return false; }
+                std::istringstream ps(line);
+                Patch p;
+                int r, g, b, camNum;
+                if (!(ps >> p.center[0] >> p.center[1] >> p.center[2] >> r >> g >> b >> camNum)) { err = "NVM: bad point line"; return false; }
+                p.color[2] = (uint8_t)r;
+                p.color[1] = (uint8_t)g;
+                p.color[0] = (uint8_t)b;
+                for (int k = 0; k < camNum; ++k) {
+                    int idx, feat;
+                    double x, y;
+                    if (!(ps >> idx >> feat >> x >> y) || idx < 0 || idx >= (int)cameras.size()) { err = "NVM: bad measurement"; return false; }
+                    p.camIdx.push_back(idx);
+                    p.imgPoint.push_back(x + cameras[idx].cols / 2);
+                    p.imgPoint.push_back(y + cameras[idx].rows / 2);
+                }
+                p.type = PMVS_TYPE_SEED;
+                p.id = nextId++;
+                setEstimatedNormal(p);               /* seed ctor, patch.cpp:26-34 */
+                patches.insert(std::pair<int, Patch>(p.id, p));
+            }
+            break;
+        }
+    }
+    reCentering();   /* mvs.cpp:161-164 */
+    return true;
+}
+
+bool MVS::loadMVS(const char *fileName) {   /* fileloader.cpp:403-472 */
+    cameras.clear();
+    patches.clear();
+    std::ifstream file(fileName, std::ios::binary);
+    if (!file.is_open()) { err = std::string("can't open MVS file ") + fileName; return false; }
+    std::string line;
+    int stage = 0;
+    while (std::getline(file, line)) {
+        std::istringstream ss(line);
+        std::string tok;
+        if (!(ss >> tok)) continue;
+        if (stage == 0) {
+            if (tok == "MVS_V2") stage = 1;
+            else if (tok == "MVS_V3") {
+                MvsConfig c;
+                file.read((char *)&c, sizeof(c));
+                if (!file) { err = "MVS: truncated config"; return false; }
+                setConfig(c);
+                stage = 1;
+            }
+            continue;
+        }
+        int num = 0;
+        ss >> num;
+        if (stage == 1) {   /* "CAMERAS n", loadMvsCamera :173-206 */
+            for (int i = 0; i < num; ++i) {
+                Camera cam;
+                int len = 0;
+                file.read((char *)&len, sizeof(int));
+                if (!file || len < 0 || len > 65536) { err = "MVS: bad camera record"; return false; }
+                cam.fileName.resize((size_t)len);
+                file.read(&cam.fileName[0], len);
+                file.read((char *)cam.center, 3 * sizeof(double));
+                file.read((char *)cam.focal, 2 * sizeof(double));
+                file.read((char *)cam.principal, 2 * sizeof(double));
+                file.read((char *)cam.quaternion, 4 * sizeof(double));
+                file.read((char *)&cam.radialDistortion, sizeof(double));
+                if (!file) { err = "MVS: truncated camera record"; return false; }
+                if (!addCamera(cam, true)) return false;
+            }
+            stage = 2;
+            continue;
+        }
+        if (stage == 2) {   /* "PATCHES n", loadMvsPatch :208-232 */
+            for (int i = 0; i < num; ++i) {
+                Patch p;
+                int camNum = 0;
+                file.read((char *)p.center, 3 * sizeof(double));
+                file.read((char *)p.normalS, 2 * sizeof(double));
+                file.read((char *)&camNum, sizeof(int));
+                if (!file || camNum < 0 || camNum > 65536) { err = "MVS: bad patch record"; return false; }
+                for (int k = 0; k < camNum; ++k) {
+                    int idx = 0;
+                    file.read((char *)&idx, sizeof(int));
+                    p.camIdx.push_back(idx);
+                }
+                file.read((char *)&p.fitness, sizeof(double));
+                file.read((char *)&p.correlation, sizeof(double));
+                if (!file) { err = "MVS: truncated patch record"; return false; }
+                spherical2Normal(p.normalS, p.normal);
+                p.type = PMVS_TYPE_SEED;      /* loader ctor marks TYPE_SEED, patch.cpp:45-59 */
+                p.id = nextId++;
+                for (size_t k = 0; k < p.camIdx.size(); ++k) {   /* setImagePoint, patch.cpp:627-653 */
+                    double pt[2] = {0, 0};
+                    if (p.camIdx[k] >= 0 && p.camIdx[k] < (int)cameras.size()) cameras[p.camIdx[k]].project(p.center, pt, 0, cfg.lodRatio);
+                    p.imgPoint.push_back(pt[0]);
+                    p.imgPoint.push_back(pt[1]);
+                }
+                patches.insert(std::pair<int, Patch>(p.id, p));
+            }
+            stage = 3;
+        }
+    }
+    return true;
+}
+
+bool MVS::writeMVS(const char *fileName) const {   /* filewriter.cpp:71-102, :26-69 */
+    std::ofstream file(fileName, std::ios::binary);
+    if (!file.is_open()) return false;
+    file << "MVS_V3" << "\n";
+    file.write((const char *)&cfg, sizeof(MvsConfig));
+    file << "CAMERAS " << (int)cameras.size() << "\n";
+    for (size_t i = 0; i < cameras.size(); ++i) {
+        const Camera &c = cameras[i];
+        const int len = (int)c.fileName.size();
+        file.write((const char *)&len, sizeof(int));
+        file.write(c.fileName.data(), len);
+        file.write((const char *)c.center, 3 * sizeof(double));
+        file.write((const char *)c.focal, 2 * sizeof(double));
+        file.write((const char *)c.principal, 2 * sizeof(double));
+        file.write((const char *)c.quaternion, 4 * sizeof(double));
+        file.write((const char *)&c.radialDistortion, sizeof(double));
+    }
+    file << "PATCHES " << (int)patches.size() << "\n";
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) {
+        const Patch &p = it->second;
+        const int camNum = (int)p.camIdx.size();
+        file.write((const char *)p.center, 3 * sizeof(double));
+        file.write((const char *)p.normalS, 2 * sizeof(double));
+        file.write((const char *)&camNum, sizeof(int));
+        for (int k = 0; k < camNum; ++k) file.write((const char *)&p.camIdx[k], sizeof(int));
+        file.write((const char *)&p.fitness, sizeof(double));
+        file.write((const char *)&p.correlation, sizeof(double));
+    }
+    return (bool)file;
+}
+
+bool MVS::writePLY(const char *fileName) const {   /* filewriter.cpp:104-139 */
+    std::ofstream file(fileName);
+    if (!file.is_open()) return false;
+    file << "ply\nformat ascii 1.0\nelement vertex " << patches.size() << "\n";
+    file << "property float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n";
+    file << "property uchar diffuse_red\nproperty uchar diffuse_green\nproperty uchar diffuse_blue\nend_header\n";
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) {
+        const Patch &p = it->second;
+        file << p.center[0] << " " << p.center[1] << " " << p.center[2] << " ";
+        file << p.normal[0] << " " << p.normal[1] << " " << p.normal[2] << " ";
+        file << int(p.color[2]) << " " << int(p.color[1]) << " " << int(p.color[0]) << "\n";
+    }
+    return (bool)file;
+}
+
+bool MVS::writePSR(const char *fileName) const {   /* filewriter.cpp:141-171 */
+    std::ofstream file(fileName, std::ios::binary);
+    if (!file.is_open()) return false;
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) {
+        const Patch &p = it->second;
+        const float v[6] = {(float)p.center[0], (float)p.center[1], (float)p.center[2], (float)p.normal[0], (float)p.normal[1], (float)p.normal[2]};
+        file.write((const char *)v, sizeof(v));
+    }
+    return (bool)file;
+}
+
+}   // namespace tmvs
