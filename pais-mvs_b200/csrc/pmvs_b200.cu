@@ -20,6 +20,9 @@
 #include "pmvs_patch.cuh"
 
 #define PMVS_VERSION "pmvs_b200 0.1 (sm_100a)"
+#ifndef PMVS_DEFAULT_LEAN
+#define PMVS_DEFAULT_LEAN false
+#endif
 
 /* ======================================================================================================= */
 __global__ void pack_quad_kernel(const uint8_t *__restrict__ grey, size_t pitch, int cols, int rows, uint32_t *__restrict__ quad) {
@@ -34,7 +37,7 @@ __global__ void pack_quad_kernel(const uint8_t *__restrict__ grey, size_t pitch,
 /* carve the dynamic shared memory of one CTA */
 struct SmemPlan {
     size_t ctaOff, viewOff, distOff, warpOff, corrOff, total;
-    size_t perWarp;      /* doubles per warp: H + xs + ys + dist */
+    size_t perWarp;      /* doubles per warp: H + xs + ys + column constants */
     int vcap, ps, nWarps;
 };
 static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t headBytes) {
@@ -51,7 +54,7 @@ static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t he
     pl.distOff = off;
     off += sizeof(double) * (size_t)ps * ps;
     pl.warpOff = off;
-    pl.perWarp = (size_t)vcap * 9 + 2 * (size_t)ps + PMVS_MAX_PARTICLES;
+    pl.perWarp = (((size_t)vcap * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_COLV_DOUBLES;
     off += sizeof(double) * pl.perWarp * nWarps;
     pl.corrOff = off;
     if (withCorr) off += sizeof(double) * (size_t)vcap * vcap;
@@ -80,7 +83,7 @@ __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArg
     W.H = base;
     W.xs = base + (size_t)a.vcap * 9;
     W.ys = W.xs + a.ps;
-    W.dist = W.ys + a.ps;
+    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES;
     return W;
 }
 
@@ -174,7 +177,8 @@ __device__ inline void patch_to_out(const PatchS &p, PmvsPatchOut &o) {
     }
 }
 
-__global__ void __launch_bounds__(256, 2) refine_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
                                                         const PmvsPatchIn *__restrict__ in, PmvsPatchOut *__restrict__ out,
                                                         uint32_t flags, int *__restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -183,7 +187,10 @@ __global__ void __launch_bounds__(256, 2) refine_kernel(const __grid_constant__ 
     double *sDistW = (double *)(smem + a.distOff);
     double *corr = (double *)(smem + a.corrOff);
     for (int k = tid; k < a.ps * a.ps; k += blockDim.x) sDistW[k] = S.distW[k];
-    if (tid == 0) c.E.view = (ViewS *)(smem + a.viewOff);
+    if (tid == 0) {
+        c.E.view = (ViewS *)(smem + a.viewOff);
+        c.part = (ParticleS *)(smem + a.ctaOff + ((sizeof(CtaS) + 15) & ~(size_t)15));
+    }
     const WarpWork W = warp_work(smem, a, warp);
     const WarpWork W0 = warp_work(smem, a, 0);
     double *hp = S.scratch + (size_t)S.scratchStride * blockIdx.x;
@@ -365,6 +372,7 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     s.distW = ctx->dDistW;
     s.nCams = ctx->nCams;
     s.seed = ctx->seed;
+    s.tune = getenv("PMVS_TUNE") ? atoi(getenv("PMVS_TUNE")) : 1;
     for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
     /* correlation scratch: one slab per resident CTA */
     const size_t stride = (size_t)ctx->vcap * ctx->cfg.patchSize * ctx->cfg.patchSize;
@@ -552,17 +560,35 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
         const int waste = ((P + w - 1) / w) * w - P;
         if (waste < bestWaste) { bestWaste = waste; NW = w; }
     }
-    SmemPlan pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, sizeof(CtaS));
-    CK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+    if (const char *envNw = getenv("PMVS_NW")) {       /* tuning override, 4..8 */
+        const int w = atoi(envNw);
+        if (w >= 4 && w <= 16) NW = w;
+    }
+    int nPart = ctx->cfg.particleNum * 2;
+    if (nPart > PMVS_MAX_PARTICLES) nPart = PMVS_MAX_PARTICLES;
+    const size_t ctaBytes = ((sizeof(CtaS) + 15) & ~(size_t)15);
+    SmemPlan pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, ctaBytes + sizeof(ParticleS) * (size_t)nPart);
+    /* two register budgets of the same kernel: 128 registers (16 warps/SM) or 96 (20 warps/SM, NW <= 5 only) */
+    typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *);
+    const char *envRegs = getenv("PMVS_REGS");
+    const bool lean = NW <= 5 && (envRegs ? atoi(envRegs) == 96 : PMVS_DEFAULT_LEAN);
+    RefineFn fn = lean ? (RefineFn)refine_kernel<160, 4> : (NW > 8 ? (RefineFn)refine_kernel<512, 1> : (RefineFn)refine_kernel<256, 2>);
+    const int warpsPerSm = lean ? 20 : 16;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     int perSm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, refine_kernel, NW * 32, pl.total));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, NW * 32, pl.total));
     if (perSm < 1) return fail(ctx, PMVS_E_UNSUPPORTED, "refine kernel does not fit on an SM with this configuration");
-    if (perSm > 16 / NW) perSm = 16 / NW;      /* 16 warps (128 registers each) per SM */
+    if (perSm > warpsPerSm / NW) perSm = warpsPerSm / NW;
     int grid = ctx->smCount * perSm;
     if (grid > ctx->scratchCtas) grid = ctx->scratchCtas;
     if (grid > n) grid = n;
+    {   /* leave everything the CTAs do not need to L1: the tap stream lives there */
+        int pct = (int)((100 * (size_t)perSm * (pl.total + 1024) + 233471) / 233472);
+        if (pct > 100) pct = 100;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     CK(cudaMemsetAsync(ctx->dCounter, 0, sizeof(int), st));
-    refine_kernel<<<grid, NW * 32, pl.total, st>>>(ctx->scene, to_args(pl), n, d_in, d_out, flags, ctx->dCounter);
+    fn<<<grid, NW * 32, pl.total, st>>>(ctx->scene, to_args(pl), n, d_in, d_out, flags, ctx->dCounter);
     ctx->launches++;
     CK(cudaGetLastError());
     return PMVS_OK;

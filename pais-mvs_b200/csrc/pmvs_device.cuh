@@ -28,6 +28,7 @@
 #define PMVS_MAX_RADIUS 31
 #define PMVS_MAX_PS (2 * PMVS_MAX_RADIUS + 1)
 #define PMVS_FULL 0xffffffffu
+#define PMVS_COLV_DOUBLES (3 * 5 * 32)
 
 struct DevLevel {
     const uint32_t *quad;
@@ -45,7 +46,7 @@ struct DevScene {
     const double *distW;       /* patchSize^2, index x*patchSize+y (mvs.cpp:104-109) */
     double *scratch;           /* per-CTA correlation windows: scratchStride doubles per CTA */
     unsigned long long scratchStride;
-    int nCams, _pad;
+    int nCams, tune;           /* tune: experiment switches (bit 0: column constants in shared memory) */
     uint64_t seed;
     double lodScale[PMVS_MAX_LEVELS];
 };
@@ -68,7 +69,7 @@ struct WarpWork {
     double *H;      /* V*9 */
     double *xs;     /* patchSize */
     double *ys;     /* patchSize */
-    double *dist;   /* PMVS_MAX_PARTICLES */
+    double *colv;   /* PMVS_COLV_DOUBLES: per-lane column constants of the unchecked loop */
 };
 
 __device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -316,6 +317,28 @@ __device__ __noinline__ bool fitness_samples(const DevScene &S, const EvalCtx &E
     return true;
 }
 
+/* exp(x) for the weights of the unchecked loop (exp(-avgSad^2/diffWeighting), exp(-1/(edge*gradientWeighting)),
+ * patch.cpp:1034,1037; x <= 0, valid up to x < 709): Cody-Waite reduction
+ * x = k ln2 + r, |r| <= ln2/2, degree-11 polynomial (Chebyshev-node interpolant of exp on that interval, relative error
+ * 1.6e-17 before rounding, coefficients from tools/exp_poly.py), scaling by exponent arithmetic. The coefficients sit in
+ * the constant bank so every fma takes its constant as an operand: no register or uniform-register traffic. Results
+ * below 2^-1020 are flushed to zero (such weights cannot matter). */
+__constant__ double kExpPoly[12] = {0x1.0000000000000p+0,  0x1.0000000000000p+0,  0x1.0000000000011p-1,  0x1.555555555555ap-3,
+                                    0x1.555555554f0bap-5,  0x1.111111110f21ep-7,  0x1.6c16c1880029fp-10, 0x1.a01a01b1461c5p-13,
+                                    0x1.a01991a10d9aep-16, 0x1.71ddf56d8deb5p-19, 0x1.28b4101c77212p-22, 0x1.af632a0f7e2cep-26};
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);      /* low word = round-to-nearest integer k */
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = kExpPoly[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, r, kExpPoly[i]);
+    const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return (x >= -707.0) ? res : ((x != x) ? x : 0.0);
+}
+
 /* 1/w for the unchecked path: MUFU.RCP64H seed r0 (~2^-20), then r0*(1+e+e^2) with e = 1-w*r0 (residual e^3); w is
  * finite, normal and > 0 there. */
 __device__ __forceinline__ double rcp_fast(double w) {
@@ -391,11 +414,20 @@ struct ColumnTaps {
     uint32_t q[VMAX];
 };
 
-template <int VMAX>
-__device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, double y, ColumnTaps<VMAX> &t) {
+__device__ __forceinline__ double lds_f64_v(unsigned a) {   /* ordered against the volatile stores below */
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64_v(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+/* SM = true: A,B,C live in a per-lane shared-memory slot (cvA + 8*(32*k + lane)) instead of registers */
+template <int VMAX, bool SM>
+__device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, unsigned cvA, double y,
+                                              ColumnTaps<VMAX> &t) {
     double w[VMAX], r[VMAX], e[VMAX];
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) w[v] = fma(lds_f64(hA + 72u * v + 56u), y, cv.C[v]);
+    for (int v = 0; v < VMAX; ++v) w[v] = fma(lds_f64(hA + 72u * v + 56u), y, SM ? lds_f64_v(cvA + 256u * (3 * v + 2)) : cv.C[v]);
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[v]) : "d"(w[v]));
     /* r = r0*(1 + e + e^2), e = 1 - w*r0: residual e^3 ~ 2^-60 from the ~2^-20 seed, three dependent fma */
@@ -407,8 +439,8 @@ __device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, const
     for (int v = 0; v < VMAX; ++v) r[v] = fma(r[v], e[v], r[v]);
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) {
-        t.fx[v] = fma(lds_f64(hA + 72u * v + 8u), y, cv.A[v]) * r[v];      /* ix */
-        t.fy[v] = fma(lds_f64(hA + 72u * v + 32u), y, cv.B[v]) * r[v];     /* iy */
+        t.fx[v] = fma(lds_f64(hA + 72u * v + 8u), y, SM ? lds_f64_v(cvA + 256u * (3 * v)) : cv.A[v]) * r[v];          /* ix */
+        t.fy[v] = fma(lds_f64(hA + 72u * v + 32u), y, SM ? lds_f64_v(cvA + 256u * (3 * v + 1)) : cv.B[v]) * r[v];     /* iy */
     }
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) {
@@ -450,10 +482,10 @@ __device__ __forceinline__ double column_blend(const ColumnTaps<VMAX> &t, double
     return sad * invV;
 }
 
-template <int VMAX>
+template <int VMAX, bool SM>
 __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
                                              const double *__restrict__ Hw, const double *__restrict__ xs,
-                                             const double *__restrict__ ys, int nx, int ny, double &fitOut, double &swOut) {
+                                             const double *__restrict__ ys, double *colv, int nx, int ny, double &fitOut, double &swOut) {
     const int lane = threadIdx.x & 31;
     const int G = 32 / nx;                         /* row groups sharing the warp */
     const int i = lane % nx, g = lane / nx;
@@ -464,12 +496,22 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
     const bool useDist = S.cfg.adaptiveDistanceEnable, useDiff = S.cfg.adaptiveDifferenceEnable, useGrad = S.cfg.adaptiveGradientEnable;
     const double invDiffW = 1.0 / S.cfg.diffWeighting, gradW = S.cfg.gradientWeighting;
     ColumnViews<VMAX> cv;
+    const unsigned cvA = smem_addr(colv) + 8u * lane;
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) {
         const unsigned h = hA + 72u * v;
-        cv.A[v] = fma(lds_f64(h), x, lds_f64(h + 16u));
-        cv.B[v] = fma(lds_f64(h + 24u), x, lds_f64(h + 40u));
-        cv.C[v] = fma(lds_f64(h + 48u), x, lds_f64(h + 64u));
+        const double a = fma(lds_f64(h), x, lds_f64(h + 16u)), b = fma(lds_f64(h + 24u), x, lds_f64(h + 40u));
+        const double c = fma(lds_f64(h + 48u), x, lds_f64(h + 64u));
+        if (SM) {
+            sts_f64_v(cvA + 256u * (3 * v), a);
+            sts_f64_v(cvA + 256u * (3 * v + 1), b);
+            sts_f64_v(cvA + 256u * (3 * v + 2), c);
+            cv.A[v] = cv.B[v] = cv.C[v] = 0;
+        } else {
+            cv.A[v] = a;
+            cv.B[v] = b;
+            cv.C[v] = c;
+        }
     }
     const int rx = __double2int_rn(x);
     const uint32_t *__restrict__ refQuad = E.refQuad;
@@ -486,8 +528,8 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
         /* both rows' tap loads are in flight before the first one is consumed */
         ColumnTaps<VMAX> ta, tb;
-        column_coords<VMAX>(viewA, hA, cv, y0, ta);
-        column_coords<VMAX>(viewA, hA, cv, y1, tb);
+        column_coords<VMAX, SM>(viewA, hA, cv, cvA, y0, ta);
+        column_coords<VMAX, SM>(viewA, hA, cv, cvA, y1, tb);
         const double s0 = column_blend<VMAX>(ta, invV);
         const double s1 = column_blend<VMAX>(tb, invV);
         double w0 = 1.0, w1 = 1.0;
@@ -495,10 +537,10 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
             w0 = lds_f64(distA + 8u * (i * ny + j));
             w1 = lds_f64(distA + 8u * (i * ny + j2));
         }
-        if (useDiff) { w0 *= exp(-s0 * s0 * invDiffW); w1 *= exp(-s1 * s1 * invDiffW); }    /* patch.cpp:1033-1035 */
+        if (useDiff) { w0 *= exp_nonpos(-s0 * s0 * invDiffW); w1 *= exp_nonpos(-s1 * s1 * invDiffW); }    /* patch.cpp:1033-1035 */
         if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
-            w0 *= exp(-1.0 / (__ldg(refEdge + rofs0) * gradW));
-            w1 *= exp(-1.0 / (__ldg(refEdge + rofs1) * gradW));
+            w0 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs0) * gradW));
+            w1 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs1) * gradW));
         }
         w0 = keep0 ? w0 : 0.0;
         w1 = keep1 ? w1 : 0.0;
@@ -559,9 +601,11 @@ __device__ __noinline__ double warp_fitness(const DevScene &S, const EvalCtx &E,
     bool ok;
     if (inside) {
         ok = true;
-        if (VCAP == 8 && E.V == 5 && nx <= 32 && nx > 0) fitness_columns<5>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
-        else if (VCAP == 8 && E.V == 4 && nx <= 32 && nx > 0) fitness_columns<4>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
-        else if (VCAP == 8 && E.V == 3 && nx <= 32 && nx > 0) fitness_columns<3>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+        if (VCAP == 8 && E.V == 5 && nx <= 32 && nx > 0) {
+            if (S.tune & 1) fitness_columns<5, true>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
+            else fitness_columns<5, false>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
+        } else if (VCAP == 8 && E.V == 4 && nx <= 32 && nx > 0) fitness_columns<4, false>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
+        else if (VCAP == 8 && E.V == 3 && nx <= 32 && nx > 0) fitness_columns<3, false>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     __syncwarp();

@@ -29,7 +29,7 @@ struct CtaS {
     PatchS p;
     EvalCtx E;
     PsoS pso;
-    ParticleS part[PMVS_MAX_PARTICLES];
+    ParticleS *part;                    /* 2*particleNum entries (seeds run 2P particles, patch.cpp:192) */
     MoveS mv;
     PmvsPatchOut out;
     int nextIdx;
