@@ -7,7 +7,7 @@
  *   mvs/camera.cpp:138-160  Camera::project            -> project_pt
  *   mvs/patch.cpp:290-330   Patch::getHomographies     -> warp_homographies
  *   mvs/patch.cpp:914-1047  PAIS::getFitness           -> warp_fitness
- *   pso/psosolver.cpp       PsoSolver (whole file)     -> pso_run / pso_move_all
+ *   pso/psosolver.cpp       PsoSolver (whole file)     -> pso_run / pso_scans / pso_apply_moves
  *
  * HBM layout. Every pyramid level of every camera is stored as a "quad" image: one 32-bit word per pixel (x,y)
  * holding the four bilinear taps g(y,x) | g(y,x+1)<<8 | g(y+1,x)<<16 | g(y+1,x+1)<<24 (edge-replicated). The
@@ -591,9 +591,10 @@ __device__ __noinline__ double warp_fitness(const DevScene &S, const EvalCtx &E,
 #pragma unroll
         for (int cidx = 0; cidx < 4; ++cidx) {
             const double x = W.xs[(cidx & 1) ? nx - 1 : 0], y = W.ys[(cidx & 2) ? ny - 1 : 0];
+            /* w > 0: lo <= n/w < hi  <=>  lo*w <= n < hi*w; the 1e-6 margin dwarfs the rounding of the products */
             const double w = H[6] * x + H[7] * y + H[8];
-            const double ix = (H[0] * x + H[1] * y + H[2]) / w, iy = (H[3] * x + H[4] * y + H[5]) / w;
-            if (!(w > 0.0 && ix >= loX && ix < hiX && iy >= loY && iy < hiY)) inside = false;
+            const double nxw = H[0] * x + H[1] * y + H[2], nyw = H[3] * x + H[4] * y + H[5];
+            if (!(w > 0.0 && nxw >= loX * w && nxw < hiX * w && nyw >= loY * w && nyw < hiY * w)) inside = false;
         }
     }
     inside = __all_sync(PMVS_FULL, inside);
@@ -762,16 +763,20 @@ __device__ __forceinline__ int pso_near_neighbor(const PsoS &ps, const ParticleS
     return best;
 }
 
-/* CTA-collective: one generation of moves. */
-__device__ __forceinline__ void pso_move_all(PsoS &ps, ParticleS *part, MoveS &mv, int it) {
+/* the four neighbourhood scans of every particle, one scan kind per warp (no divergence); no barrier inside */
+__device__ __forceinline__ void pso_scans(const PsoS &ps, const ParticleS *part, MoveS &mv) {
     const int P = ps.P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-    for (int kind = warp; kind < 4; kind += NW)          /* one scan kind per warp: no divergence */
+    for (int kind = warp; kind < 4; kind += NW)
         for (int i = lane; i < P; i += 32) {
             if (kind == 0) mv.lBest[i] = pso_local_best(ps, part, i);
             else mv.nIdx[kind - 1][i] = pso_near_neighbor(ps, part, i, kind - 1);
         }
-    __syncthreads();
+}
+
+/* velocity / position update of generation `it`, thread = particle (psosolver.cpp:225-262); ends with a barrier */
+__device__ __forceinline__ void pso_apply_moves(PsoS &ps, ParticleS *part, const MoveS &mv, int it) {
+    const int P = ps.P;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         ParticleS &me = part[i];
         const uint64_t c0 = (uint64_t)ps.drawBase + 4ull * ((uint64_t)it * P + i);
@@ -845,16 +850,29 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
     }
     evals += P;
     __syncthreads();
-    if (tid == 0) {                                                   /* run :288-291 */
-        ps.gBestIdx = 0;
-        ps.gBestFitness = part[0].pbf;
-        ps.iteration = 0;
-        pso_update_gbest(ps, part);
-    }
-    __syncthreads();
+    /*
+     * run (:286-306), three barriers per generation. After the evaluations of generation it-1:
+     *   phase A  one warp does the sequential bookkeeping — updateGbest (:137-149) and the inertia step (:304) of
+     *            generation it-1, then the convergence test of generation it (:295, sequential sums :70-92) — while
+     *            four other warps run the neighbourhood scans of generation it (they read pBest / pBestFitness only);
+     *   phase B  velocity / position update;   phase C  evaluations.
+     */
+    const int bookWarp = NW > 4 ? 4 : 0;
     int it = 0;
-    for (; it < ps.maxIter; ++it) {
-        if (warp == 0) {                                              /* :295, :70-92 (sequential sums) */
+    for (;;) {
+        if (it < ps.maxIter) pso_scans(ps, part, mv);
+        if (warp == bookWarp) {
+            if (lane == 0) {
+                if (it == 0) {                                        /* :288-291 */
+                    ps.gBestIdx = 0;
+                    ps.gBestFitness = part[0].pbf;
+                } else {
+                    const double niw = ps.iw - 1.0 / ps.maxIter;      /* :304 (after updateGbest, which does not read iw) */
+                    ps.iw = niw > 0.4 ? niw : 0.4;
+                }
+                pso_update_gbest(ps, part);
+            }
+            __syncwarp();
             double index = 0;
             if (lane == 0) {
                 const double *g = part[ps.gBestIdx].pBest;
@@ -870,8 +888,8 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
             if (lane == 0) ps.converged = (disp < 0.01 && velo < 0.01) ? 1 : 0;
         }
         __syncthreads();
-        if (ps.converged) break;
-        pso_move_all(ps, part, mv, it);                                                  /* moveParticles */
+        if (it >= ps.maxIter || ps.converged) break;
+        pso_apply_moves(ps, part, mv, it);                                               /* moveParticles */
         for (int p = warp; p < P; p += NW) {                                             /* updateFitness :121-135 */
             const double f = eval(part[p].pos);
             if (lane == 0) {
@@ -885,13 +903,7 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
         }
         evals += P;
         __syncthreads();
-        if (tid == 0) {
-            ps.iteration = it;                                                           /* value seen by updateGbest */
-            pso_update_gbest(ps, part);
-            const double niw = ps.iw - 1.0 / ps.maxIter;                                 /* :304 */
-            ps.iw = niw > 0.4 ? niw : 0.4;
-        }
-        __syncthreads();
+        ++it;
     }
     if (tid == 0) ps.iteration = it;
     __syncthreads();
