@@ -98,6 +98,14 @@ typedef struct PmvsLevel {
     const double  *edge;
 } PmvsLevel;
 
+/* Writable host level for pmvs_build_pyramid. */
+typedef struct PmvsLevelOut {
+    int32_t cols, rows;
+    int64_t pitch;
+    uint8_t *grey;
+    double  *edge;
+} PmvsLevelOut;
+
 /* Camera (TMVS/mvs/camera.h:15-72) after construction (camera.cpp:45-136): matrices row-major. */
 typedef struct PmvsCamera {
     double focal[2];
@@ -169,10 +177,23 @@ typedef struct PmvsPatchOut {
 
 typedef struct pmvs_ctx pmvs_ctx;   /* opaque; owns all device memory; one per GPU; not thread-safe */
 
+/* Number of pyramid levels of a cols x rows image and their sizes (camera.cpp:63-64; cv::resize rounds the size).
+ * Host-only helper. levelCols / levelRows: PMVS_MAX_LEVELS entries or NULL. */
+int pmvs_pyramid_levels(int cols, int rows, double lodRatio, int cfgMaxLOD, int *maxLOD, int32_t *levelCols,
+                        int32_t *levelRows);
+
+/* The Camera ctor's pyramid (camera.cpp:63-92) built on `device`: level l = INTER_AREA resize of level 0 by
+ * lodRatio^l, edge = min-max normalised [-1,0,1] gradient magnitude. levels[0..maxLOD]: caller-allocated host arrays
+ * with cols/rows from pmvs_pyramid_levels (levels[0].grey may be NULL); edge arrays required iff withEdge. */
+int pmvs_build_pyramid(int device, const uint8_t *grey0, int cols, int rows, int64_t pitch, double lodRatio, int maxLOD,
+                       int withEdge, PmvsLevelOut *levels);
+
 /* Upload config + cameras + pyramids to `device` and build the derived tables
  * (distance weighting MVS::initPatchDistanceWeighting mvs.cpp:97-114; lodRatio^l).
  * rngSeed keys the counter-based replacement of the reference's srand(time)+rand()
- * (psosolver.cpp:60-68). */
+ * (psosolver.cpp:60-68). Level 0 of every camera must be given; a level l >= 1 whose `grey` is NULL is built on the
+ * device from level 0 (its cols/rows may be 0 or must equal pmvs_pyramid_levels'), and a NULL `edge` is built on the
+ * device when cfg->adaptiveGradientEnable is set. */
 int pmvs_create(pmvs_ctx **out, const PmvsConfig *cfg, int nCams, const PmvsCamera *cams,
                 int device, uint64_t rngSeed);
 

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "pmvs_patch.cuh"
+#include "pmvs_pyramid.cuh"
 
 #define PMVS_VERSION "pmvs_b200 0.1 (sm_100a)"
 #ifndef PMVS_DEFAULT_LEAN
@@ -409,6 +410,81 @@ void pmvs_destroy(pmvs_ctx *ctx) {
     delete ctx;
 }
 
+
+/* ---- device pyramid builder (camera.cpp:63-92), shared by pmvs_create and pmvs_build_pyramid ----------------- */
+static inline int cv_round(double v) { return (int)std::nearbyint(v); }
+
+struct DevU8 {
+    uint8_t *p = nullptr;
+    size_t pitch = 0;
+    int cols = 0, rows = 0;
+};
+
+static cudaError_t upload_u8(const uint8_t *host, int64_t hpitch, int cols, int rows, DevU8 &d, cudaStream_t st) {
+    cudaError_t e = cudaMallocPitch(&d.p, &d.pitch, (size_t)cols, (size_t)rows);
+    if (e != cudaSuccess) return e;
+    d.cols = cols;
+    d.rows = rows;
+    return cudaMemcpy2DAsync(d.p, d.pitch, host, (size_t)hpitch, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice, st);
+}
+
+/* level l (cols x rows) = INTER_AREA resize of `src` by factor f; launches counted in *launches */
+static cudaError_t resize_level(const DevU8 &src, double f, int dcols, int drows, DevU8 &dst, cudaStream_t st, int64_t *launches) {
+    AreaTab tx, ty;
+    const double scale = 1.0 / f;
+    build_area_tab(src.cols, dcols, scale, tx);
+    build_area_tab(src.rows, drows, scale, ty);
+    cudaError_t e = cudaMallocPitch(&dst.p, &dst.pitch, (size_t)dcols, (size_t)drows);
+    if (e != cudaSuccess) return e;
+    dst.cols = dcols;
+    dst.rows = drows;
+    const size_t nI = (size_t)2 * (dcols + drows), nW = tx.w.size() + ty.w.size();
+    int *dI = nullptr;
+    float *dW = nullptr;
+    if ((e = cudaMalloc(&dI, nI * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&dW, nW * sizeof(float))) != cudaSuccess) { cudaFree(dI); return e; }
+    std::vector<int> hI;
+    hI.insert(hI.end(), tx.start.begin(), tx.start.end());
+    hI.insert(hI.end(), tx.count.begin(), tx.count.end());
+    hI.insert(hI.end(), ty.start.begin(), ty.start.end());
+    hI.insert(hI.end(), ty.count.begin(), ty.count.end());
+    std::vector<float> hW(tx.w);
+    hW.insert(hW.end(), ty.w.begin(), ty.w.end());
+    e = cudaMemcpyAsync(dI, hI.data(), nI * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dW, hW.data(), nW * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        dim3 block(32, 8), grid((dcols + 31) / 32, (drows + 7) / 8);
+        resize_area_kernel<<<grid, block, 0, st>>>(src.p, src.pitch, src.cols, src.rows, dst.p, dst.pitch, dcols, drows, dI, dI + dcols,
+                                                    dW, tx.maxTaps, dI + 2 * dcols, dI + 2 * dcols + drows, dW + tx.w.size(), ty.maxTaps);
+        ++*launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);     /* the host tables must outlive the copies */
+    cudaFree(dI);
+    cudaFree(dW);
+    return e;
+}
+
+/* min-max normalised gradient magnitude of one level into `edge` (cols*rows doubles on the device) */
+static cudaError_t edge_level(const DevU8 &g, double *edge, unsigned long long *dMinMax, cudaStream_t st, int64_t *launches) {
+    const unsigned long long init[2] = {~0ull, 0ull};
+    cudaError_t e = cudaMemcpyAsync(dMinMax, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    dim3 grid((g.cols + 255) / 256, g.rows < 1024 ? g.rows : 1024);
+    edge_minmax_kernel<<<grid, 256, 0, st>>>(g.p, g.pitch, g.cols, g.rows, dMinMax);
+    edge_normalise_kernel<<<grid, 256, 0, st>>>(g.p, g.pitch, g.cols, g.rows, dMinMax, edge);
+    *launches += 2;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);     /* `init` is a stack buffer */
+    return e;
+}
+
+static void level_dims(int cols0, int rows0, double lodRatio, int l, int &c, int &r) {   /* cv::resize rounds the size */
+    const double f = pow(lodRatio, l);
+    c = l == 0 ? cols0 : cv_round(cols0 * f);
+    r = l == 0 ? rows0 : cv_round(rows0 * f);
+}
+
 static int create_impl(pmvs_ctx *ctx, const PmvsConfig *cfg, int nCams, const PmvsCamera *cams, int device, uint64_t rngSeed) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -445,37 +521,62 @@ static int create_impl(pmvs_ctx *ctx, const PmvsConfig *cfg, int nCams, const Pm
         memcpy(d.pp, c.principal, sizeof(d.pp));
         if (c.maxLOD < 0 || c.maxLOD >= PMVS_MAX_LEVELS) return fail(ctx, PMVS_E_ARG, "camera maxLOD out of range");
         d.maxLOD = c.maxLOD;
-        for (int l = 0; l <= c.maxLOD; ++l) {
+        /* level 0 must come from the host; any further level whose grey pointer is NULL is built on the device
+         * (INTER_AREA from level 0, camera.cpp:81-85); edges likewise when the config needs them (camera.cpp:71-92) */
+        const PmvsLevel &L0 = c.level[0];
+        if (L0.cols <= 0 || L0.rows <= 0 || !L0.grey || L0.pitch < L0.cols) return fail(ctx, PMVS_E_ARG, "bad pyramid level 0");
+        DevU8 g0;
+        e = upload_u8(L0.grey, L0.pitch, L0.cols, L0.rows, g0, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(g0.p); return fail(ctx, PMVS_E_CUDA, std::string("level upload: ") + cudaGetErrorString(e)); }
+        unsigned long long *dMinMax = nullptr;
+        for (int l = 0; l <= c.maxLOD && e == cudaSuccess; ++l) {
             const PmvsLevel &L = c.level[l];
-            if (L.cols <= 0 || L.rows <= 0 || !L.grey || L.pitch < L.cols) return fail(ctx, PMVS_E_ARG, "bad pyramid level");
-            uint8_t *tmp = nullptr;
+            DevU8 gl;
+            if (l == 0) gl = g0;
+            else if (L.grey) {
+                if (L.cols <= 0 || L.rows <= 0 || L.pitch < L.cols) { cudaFree(g0.p); return fail(ctx, PMVS_E_ARG, "bad pyramid level"); }
+                e = upload_u8(L.grey, L.pitch, L.cols, L.rows, gl, ctx->stream);
+            } else {
+                int lc, lr;
+                level_dims(L0.cols, L0.rows, cfg->lodRatio, l, lc, lr);
+                if ((L.cols > 0 && L.cols != lc) || (L.rows > 0 && L.rows != lr) || lc <= 0 || lr <= 0) {
+                    cudaFree(g0.p);
+                    return fail(ctx, PMVS_E_ARG, "pyramid level size does not match round(size0 * lodRatio^l)");
+                }
+                e = resize_level(g0, pow(cfg->lodRatio, l), lc, lr, gl, ctx->stream, &ctx->launches);
+            }
             uint32_t *quad = nullptr;
-            size_t dpitch = 0;
-            CK(cudaMallocPitch(&tmp, &dpitch, (size_t)L.cols, (size_t)L.rows));
-            e = cudaMalloc(&quad, (size_t)L.cols * L.rows * sizeof(uint32_t));
-            if (e != cudaSuccess) { cudaFree(tmp); return fail(ctx, PMVS_E_NOMEM, "cudaMalloc(quad level) failed"); }
-            ctx->allocs.push_back(quad);
-            e = cudaMemcpy2DAsync(tmp, dpitch, L.grey, (size_t)L.pitch, (size_t)L.cols, (size_t)L.rows, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaMalloc(&quad, (size_t)gl.cols * gl.rows * sizeof(uint32_t));
             if (e == cudaSuccess) {
-                dim3 grid((L.cols + 255) / 256, L.rows);
-                pack_quad_kernel<<<grid, 256, 0, ctx->stream>>>(tmp, dpitch, L.cols, L.rows, quad);
+                ctx->allocs.push_back(quad);
+                dim3 grid((gl.cols + 255) / 256, gl.rows);
+                pack_quad_kernel<<<grid, 256, 0, ctx->stream>>>(gl.p, gl.pitch, gl.cols, gl.rows, quad);
                 ctx->launches++;
-                e = cudaStreamSynchronize(ctx->stream);
+                e = cudaGetLastError();
             }
-            cudaFree(tmp);
-            if (e != cudaSuccess) return fail(ctx, PMVS_E_CUDA, std::string("level upload: ") + cudaGetErrorString(e));
             d.level[l].quad = quad;
-            d.level[l].cols = L.cols;
-            d.level[l].rows = L.rows;
+            d.level[l].cols = gl.cols;
+            d.level[l].rows = gl.rows;
             d.level[l].edge = nullptr;
-            if (L.edge) {
+            if (e == cudaSuccess && (L.edge || cfg->adaptiveGradientEnable)) {
                 double *edge = nullptr;
-                CK(cudaMalloc(&edge, (size_t)L.cols * L.rows * sizeof(double)));
-                ctx->allocs.push_back(edge);
-                CK(cudaMemcpy(edge, L.edge, (size_t)L.cols * L.rows * sizeof(double), cudaMemcpyHostToDevice));
-                d.level[l].edge = edge;
+                e = cudaMalloc(&edge, (size_t)gl.cols * gl.rows * sizeof(double));
+                if (e == cudaSuccess) {
+                    ctx->allocs.push_back(edge);
+                    d.level[l].edge = edge;
+                    if (L.edge) e = cudaMemcpyAsync(edge, L.edge, (size_t)gl.cols * gl.rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+                    else {
+                        if (!dMinMax) e = cudaMalloc(&dMinMax, 2 * sizeof(unsigned long long));
+                        if (e == cudaSuccess) e = edge_level(gl, edge, dMinMax, ctx->stream, &ctx->launches);
+                    }
+                }
             }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (l > 0) cudaFree(gl.p);
         }
+        cudaFree(g0.p);
+        if (dMinMax) cudaFree(dMinMax);
+        if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? PMVS_E_NOMEM : PMVS_E_CUDA, std::string("pyramid build: ") + cudaGetErrorString(e));
     }
     CK(cudaMalloc(&ctx->dCams, sizeof(DevCamera) * (size_t)nCams));
     CK(cudaMemcpy(ctx->dCams, hc.data(), sizeof(DevCamera) * (size_t)nCams, cudaMemcpyHostToDevice));
@@ -619,6 +720,65 @@ int pmvs_refine_batch(pmvs_ctx *ctx, int n, const PmvsPatchIn *in, PmvsPatchOut 
     CK(cudaMemcpyAsync(out, ctx->dOut, sizeof(PmvsPatchOut) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return PMVS_OK;
+}
+
+/* camera.cpp:63-64 + cv::resize size rounding: host-only helper, no device needed */
+int pmvs_pyramid_levels(int cols, int rows, double lodRatio, int cfgMaxLOD, int *maxLOD, int32_t *levelCols, int32_t *levelRows) {
+    if (cols <= 0 || rows <= 0 || !(lodRatio > 0.0 && lodRatio < 1.0) || !maxLOD) return PMVS_E_ARG;
+    int m = (int)(log((double)(cols > rows ? cols : rows)) / log(1.0 / lodRatio));
+    if (m > cfgMaxLOD) m = cfgMaxLOD;
+    if (m >= PMVS_MAX_LEVELS) m = PMVS_MAX_LEVELS - 1;
+    if (m < 0) m = 0;
+    *maxLOD = m;
+    for (int l = 0; l <= m; ++l) {
+        int c, r;
+        level_dims(cols, rows, lodRatio, l, c, r);
+        if (levelCols) levelCols[l] = c;
+        if (levelRows) levelRows[l] = r;
+    }
+    return PMVS_OK;
+}
+
+/* The pyramid of one camera built on `device` and copied back to caller-allocated host levels (levels[0].grey may be
+ * NULL: level 0 is the input). Used by tests and by hosts that want the arrays; pmvs_create builds missing levels
+ * itself without a host round trip. */
+int pmvs_build_pyramid(int device, const uint8_t *grey0, int cols, int rows, int64_t pitch, double lodRatio, int maxLOD, int withEdge,
+                       PmvsLevelOut *levels) {
+    if (!grey0 || cols <= 0 || rows <= 0 || pitch < cols || maxLOD < 0 || maxLOD >= PMVS_MAX_LEVELS || !levels) return PMVS_E_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PMVS_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return PMVS_E_CUDA;
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return PMVS_E_CUDA;
+    int64_t launches = 0;
+    DevU8 g0;
+    unsigned long long *dMinMax = nullptr;
+    double *dEdge = nullptr;
+    cudaError_t e = upload_u8(grey0, pitch, cols, rows, g0, st);
+    if (e == cudaSuccess && withEdge) e = cudaMalloc(&dMinMax, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess && withEdge) e = cudaMalloc(&dEdge, (size_t)cols * rows * sizeof(double));
+    int rc = PMVS_OK;
+    for (int l = 0; l <= maxLOD && e == cudaSuccess; ++l) {
+        int lc, lr;
+        level_dims(cols, rows, lodRatio, l, lc, lr);
+        PmvsLevelOut &L = levels[l];
+        if (L.cols != lc || L.rows != lr || (l > 0 && (!L.grey || L.pitch < lc)) || (withEdge && !L.edge)) { rc = PMVS_E_ARG; break; }
+        DevU8 gl = g0;
+        if (l > 0) e = resize_level(g0, pow(lodRatio, l), lc, lr, gl, st, &launches);
+        if (e == cudaSuccess && l > 0) e = cudaMemcpy2DAsync(L.grey, (size_t)L.pitch, gl.p, gl.pitch, (size_t)lc, (size_t)lr, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && withEdge) {
+            e = edge_level(gl, dEdge, dMinMax, st, &launches);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(L.edge, dEdge, (size_t)lc * lr * sizeof(double), cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (l > 0) cudaFree(gl.p);
+    }
+    cudaFree(g0.p);
+    cudaFree(dMinMax);
+    cudaFree(dEdge);
+    cudaStreamDestroy(st);
+    if (rc != PMVS_OK) return rc;
+    return e == cudaSuccess ? PMVS_OK : (e == cudaErrorMemoryAllocation ? PMVS_E_NOMEM : PMVS_E_CUDA);
 }
 
 /* test support: the swarm alone on analytic functions. L,U,init: n*3; keys,maxIter,P,fn,hasInit: n. Outputs:

@@ -68,10 +68,8 @@ struct CellMap {   /* TMVS/mvs/cellmap.{h,cpp} */
 void setInitConfig(MvsConfig &c);                                   /* TMVS.cpp:26-52 */
 bool loadConfig(const char *fileName, MvsConfig &c);                /* fileloader.cpp:474-565 */
 
-/* image helpers (camera.cpp:51-92) */
+/* image reader (camera.cpp:51-69; the pyramid itself is built on the GPU) */
 bool readPnm(const std::string &path, int &cols, int &rows, std::vector<uint8_t> &grey, std::vector<uint8_t> &rgb);
-void resizeArea(const std::vector<uint8_t> &src, int cols, int rows, double f, std::vector<uint8_t> &dst, int &dcols, int &drows);
-void edgeImage(const std::vector<uint8_t> &grey, int cols, int rows, std::vector<double> &edge);
 
 class MVS {
 public:

@@ -94,7 +94,7 @@ bool loadConfig(const char *fileName, MvsConfig &c) {   /* TMVS/io/fileloader.cp
 }
 
 /* ---------------------------------------------------------------------------------------------------------
- * images (the reference uses cv::imread / resize / Sobel, camera.cpp:51-92)
+ * images (the reference uses cv::imread, camera.cpp:51-69; resize / Sobel run on the GPU, csrc/pmvs_pyramid.cuh)
  * ------------------------------------------------------------------------------------------------------- */
 static bool pnmToken(std::istream &in, std::string &tok) {
     tok.clear();
@@ -132,67 +132,6 @@ bool readPnm(const std::string &path, int &cols, int &rows, std::vector<uint8_t>
         for (size_t i = 0; i < n; ++i) grey[i] = (uint8_t)((rgb[3 * i] * 4899 + rgb[3 * i + 1] * 9617 + rgb[3 * i + 2] * 1868 + 8192) >> 14);
     }
     return true;
-}
-
-/* cv::resize(..., INTER_AREA) for a non-integer scale < 1 (imgproc resize.cpp, computeResizeAreaTab) */
-static void areaTab(int ssize, int dsize, double scale, std::vector<int> &start, std::vector<std::vector<float> > &w) {
-    start.assign(dsize, 0);
-    w.assign(dsize, std::vector<float>());
-    for (int dx = 0; dx < dsize; ++dx) {
-        const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
-        const double cell = std::min(scale, ssize - fsx1);
-        int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
-        sx2 = std::min(sx2, ssize - 1);
-        sx1 = std::min(sx1, sx2);
-        int first = sx1;
-        if (sx1 - fsx1 > 1e-3) { first = sx1 - 1; w[dx].push_back((float)((sx1 - fsx1) / cell)); }
-        start[dx] = first;
-        for (int sx = sx1; sx < sx2; ++sx) w[dx].push_back((float)(1.0 / cell));
-        if (fsx2 - sx2 > 1e-3) w[dx].push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell));
-    }
-}
-
-void resizeArea(const std::vector<uint8_t> &src, int cols, int rows, double f, std::vector<uint8_t> &dst, int &dcols, int &drows) {
-    dcols = cvRound(cols * f);
-    drows = cvRound(rows * f);
-    const double scale = 1.0 / f;
-    std::vector<int> xs, ys;
-    std::vector<std::vector<float> > wx, wy;
-    areaTab(cols, dcols, scale, xs, wx);
-    areaTab(rows, drows, scale, ys, wy);
-    std::vector<float> tmp((size_t)rows * dcols);
-    for (int y = 0; y < rows; ++y)
-        for (int dx = 0; dx < dcols; ++dx) {
-            float acc = 0;
-            for (size_t k = 0; k < wx[dx].size(); ++k) acc += wx[dx][k] * src[(size_t)y * cols + xs[dx] + (int)k];
-            tmp[(size_t)y * dcols + dx] = acc;
-        }
-    dst.resize((size_t)drows * dcols);
-    for (int dy = 0; dy < drows; ++dy)
-        for (int dx = 0; dx < dcols; ++dx) {
-            float acc = 0;
-            for (size_t k = 0; k < wy[dy].size(); ++k) acc += wy[dy][k] * tmp[(size_t)(ys[dy] + (int)k) * dcols + dx];
-            const int v = cvRound(acc);
-            dst[(size_t)dy * dcols + dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
-        }
-}
-
-/* Sobel ksize=1 ([-1,0,1], BORDER_REFLECT_101) magnitude, min-max normalised (camera.cpp:71-78) */
-void edgeImage(const std::vector<uint8_t> &g, int cols, int rows, std::vector<double> &edge) {
-    edge.resize((size_t)cols * rows);
-    double mn = DBL_MAX, mx = -DBL_MAX;
-    for (int y = 0; y < rows; ++y)
-        for (int x = 0; x < cols; ++x) {
-            const int xl = x == 0 ? (cols > 1 ? 1 : 0) : x - 1, xr = x == cols - 1 ? (cols > 1 ? cols - 2 : 0) : x + 1;
-            const int yu = y == 0 ? (rows > 1 ? 1 : 0) : y - 1, yd = y == rows - 1 ? (rows > 1 ? rows - 2 : 0) : y + 1;
-            const double gx = (double)g[(size_t)y * cols + xr] - g[(size_t)y * cols + xl];
-            const double gy = (double)g[(size_t)yd * cols + x] - g[(size_t)yu * cols + x];
-            const double e = sqrt(gx * gx + gy * gy);
-            edge[(size_t)y * cols + x] = e;
-            mn = std::min(mn, e);
-            mx = std::max(mx, e);
-        }
-    for (size_t i = 0; i < edge.size(); ++i) edge[i] = (edge[i] - mn) / (mx - mn);
 }
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -243,17 +182,16 @@ bool MVS::addCamera(Camera &cam, bool loadImage) {
             err = "can't read image " + base + " (PGM/PPM expected; see tools/convert_images.py)";
             return false;
         }
-        int m = (int)(log((double)std::max(cam.cols, cam.rows)) / log(1.0 / cfg.lodRatio));   /* camera.cpp:63-64 */
-        cam.maxLOD = std::min(m, (int)cfg.maxLOD);
-        if (cam.maxLOD >= PMVS_MAX_LEVELS) cam.maxLOD = PMVS_MAX_LEVELS - 1;
+        /* camera.cpp:63-92: level sizes here, the levels themselves (INTER_AREA resize, edge pyramid) are built on the
+         * GPU by pmvs_create from level 0 — the host only ever reads level 0 (runtimeFiltering, mvs.cpp:851-863) */
+        int32_t lc[PMVS_MAX_LEVELS], lr[PMVS_MAX_LEVELS];
+        if (pmvs_pyramid_levels(cam.cols, cam.rows, cfg.lodRatio, cfg.maxLOD, &cam.maxLOD, lc, lr) != PMVS_OK) {
+            err = "bad image size / lodRatio for " + base;
+            return false;
+        }
         cam.pyramid.resize(cam.maxLOD + 1);
-        cam.pyramid[0].cols = cam.cols;
-        cam.pyramid[0].rows = cam.rows;
+        for (int i = 0; i <= cam.maxLOD; ++i) { cam.pyramid[i].cols = lc[i]; cam.pyramid[i].rows = lr[i]; }
         cam.pyramid[0].grey = grey;
-        for (int i = 1; i <= cam.maxLOD; ++i)
-            resizeArea(grey, cam.cols, cam.rows, pow(cfg.lodRatio, i), cam.pyramid[i].grey, cam.pyramid[i].cols, cam.pyramid[i].rows);
-        if (cfg.adaptiveGradientEnable)      /* the edge pyramid is only read at patch.cpp:1037 */
-            for (int i = 0; i <= cam.maxLOD; ++i) edgeImage(cam.pyramid[i].grey, cam.pyramid[i].cols, cam.pyramid[i].rows, cam.pyramid[i].edge);
     }
     if (cam.principal[0] < 0 && cam.principal[1] < 0) {   /* camera.cpp:101-106 */
         cam.principal[0] = cam.cols >> 1;
@@ -587,8 +525,8 @@ bool MVS::ensureContext() {
             r.level[l].cols = c.pyramid[l].cols;
             r.level[l].rows = c.pyramid[l].rows;
             r.level[l].pitch = c.pyramid[l].cols;
-            r.level[l].grey = c.pyramid[l].grey.data();
-            r.level[l].edge = c.pyramid[l].edge.empty() ? nullptr : c.pyramid[l].edge.data();
+            r.level[l].grey = c.pyramid[l].grey.empty() ? nullptr : c.pyramid[l].grey.data();   /* NULL: built on the device */
+            r.level[l].edge = nullptr;
         }
     }
     const int rc = pmvs_create(&ctx, &cfg, (int)recs.size(), recs.data(), device, rngSeed);

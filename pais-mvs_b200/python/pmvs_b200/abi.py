@@ -35,6 +35,11 @@ class PmvsLevel(C.Structure):
                 ("grey", C.c_void_p), ("edge", C.c_void_p)]
 
 
+class PmvsLevelOut(C.Structure):
+    _fields_ = [("cols", C.c_int32), ("rows", C.c_int32), ("pitch", C.c_int64),
+                ("grey", C.c_void_p), ("edge", C.c_void_p)]
+
+
 class PmvsCamera(C.Structure):
     _fields_ = [
         ("focal", C.c_double * 2), ("principal", C.c_double * 2), ("center", C.c_double * 3),

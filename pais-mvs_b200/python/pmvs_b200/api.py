@@ -93,3 +93,37 @@ class PatchRefiner:
             pp = [list(parts[(i * 64 + k) * 8:(i * 64 + k) * 8 + 8]) for k in range(problems[i]["P"])]
             res.append(dict(gbest=list(gb[3 * i:3 * i + 3]), gbestFitness=gf[i], iterations=it[i], particles=pp))
         return res
+
+
+def pyramid_levels(cols, rows, lod_ratio, cfg_max_lod):
+    """camera.cpp:63-64: (maxLOD, [(cols, rows) per level]) — host-only."""
+    L = load()
+    m = C.c_int()
+    lc = (C.c_int32 * abi.MAX_LEVELS)()
+    lr = (C.c_int32 * abi.MAX_LEVELS)()
+    rc = L.pmvs_pyramid_levels(cols, rows, lod_ratio, cfg_max_lod, C.byref(m), lc, lr)
+    if rc != 0:
+        raise PmvsError(rc, "pmvs_pyramid_levels: bad arguments")
+    return m.value, [(lc[i], lr[i]) for i in range(m.value + 1)]
+
+
+def build_pyramid(grey0, lod_ratio, cfg_max_lod, with_edge=True, device=0):
+    """The Camera ctor's pyramid (camera.cpp:63-92) built on the GPU; returns [(grey u8, edge f64|None)] like
+    scene.build_pyramid."""
+    import numpy as np
+    L = load()
+    rows, cols = grey0.shape
+    max_lod, dims = pyramid_levels(cols, rows, lod_ratio, cfg_max_lod)
+    levels = (abi.PmvsLevelOut * (max_lod + 1))()
+    out = []
+    for l, (c, r) in enumerate(dims):
+        g = np.ascontiguousarray(grey0) if l == 0 else np.empty((r, c), dtype=np.uint8)
+        e = np.empty((r, c), dtype=np.float64) if with_edge else None
+        levels[l].cols, levels[l].rows, levels[l].pitch = c, r, g.strides[0]
+        levels[l].grey = g.ctypes.data
+        levels[l].edge = e.ctypes.data if with_edge else None
+        out.append((g, e))
+    rc = L.pmvs_build_pyramid(device, out[0][0].ctypes.data, cols, rows, out[0][0].strides[0], lod_ratio, max_lod, int(with_edge), levels)
+    if rc != 0:
+        raise PmvsError(rc, "pmvs_build_pyramid failed")
+    return out

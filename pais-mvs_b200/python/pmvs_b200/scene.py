@@ -65,8 +65,12 @@ def camera_max_lod(cols, rows, cfg):
 # pyramids (camera.cpp:63-92)
 # ---------------------------------------------------------------------------------------------------------
 def _area_tab(ssize, dsize, scale):
-    """Weights of OpenCV's INTER_AREA for a non-integer scale (imgproc resize.cpp computeResizeAreaTab)."""
-    W = np.zeros((dsize, ssize), dtype=np.float32)
+    """OpenCV's INTER_AREA table for one axis and a non-integer scale (imgproc computeResizeAreaTab): per destination
+    index the first source index, the tap count and the float32 weights."""
+    max_taps = int(math.ceil(scale)) + 2
+    start = np.zeros(dsize, dtype=np.int64)
+    count = np.zeros(dsize, dtype=np.int64)
+    W = np.zeros((dsize, max_taps), dtype=np.float32)
     for dx in range(dsize):
         fsx1 = dx * scale
         fsx2 = fsx1 + scale
@@ -75,23 +79,43 @@ def _area_tab(ssize, dsize, scale):
         sx2 = int(math.floor(fsx2))
         sx2 = min(sx2, ssize - 1)
         sx1 = min(sx1, sx2)
+        n, first = 0, sx1
         if sx1 - fsx1 > 1e-3:
-            W[dx, sx1 - 1] += (sx1 - fsx1) / cell
+            first = sx1 - 1
+            W[dx, n] = (sx1 - fsx1) / cell
+            n += 1
         for sx in range(sx1, sx2):
-            W[dx, sx] += 1.0 / cell
+            W[dx, n] = 1.0 / cell
+            n += 1
         if fsx2 - sx2 > 1e-3:
-            W[dx, sx2] += min(min(fsx2 - sx2, 1.0), cell) / cell
-    return W
+            W[dx, n] = min(min(fsx2 - sx2, 1.0), cell) / cell
+            n += 1
+        start[dx], count[dx] = first, n
+    return start, count, W
 
 
 def resize_area(img, f):
-    """cv::resize(img, Size(), f, f, INTER_AREA) for u8 single-channel, f < 1 (camera.cpp:85)."""
+    """cv::resize(img, Size(), f, f, INTER_AREA) for u8 single-channel, f < 1 (camera.cpp:85): float32 weighted
+    horizontal sums per source row, then float32 weighted vertical sums, each accumulated in source order (the order
+    csrc/pmvs_pyramid.cuh and host/tmvs_lib.cpp use, so all three agree bit for bit), round half to even, saturate."""
     rows, cols = img.shape
     dcols, drows = int(np.rint(cols * f)), int(np.rint(rows * f))
     scale = 1.0 / f
-    Wx = _area_tab(cols, dcols, scale)
-    Wy = _area_tab(rows, drows, scale)
-    out = Wy @ img.astype(np.float32) @ Wx.T
+    xs, xn, Wx = _area_tab(cols, dcols, scale)
+    ys, yn, Wy = _area_tab(rows, drows, scale)
+    src = img.astype(np.float32)
+    tmp = np.zeros((rows, dcols), dtype=np.float32)
+    for k in range(Wx.shape[1]):
+        m = k < xn
+        if not m.any():
+            break
+        tmp[:, m] = tmp[:, m] + Wx[m, k][None, :] * src[:, xs[m] + k]
+    out = np.zeros((drows, dcols), dtype=np.float32)
+    for k in range(Wy.shape[1]):
+        m = k < yn
+        if not m.any():
+            break
+        out[m, :] = out[m, :] + Wy[m, k][:, None] * tmp[ys[m] + k, :]
     return np.clip(np.rint(out), 0, 255).astype(np.uint8)
 
 

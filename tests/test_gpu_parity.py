@@ -284,3 +284,36 @@ def test_refine_properties_full_size():
             checked += 1
             assert abs(f[i] - q.fitness) <= 1e-9 * max(1.0, q.fitness), (i, f[i], q.fitness)
     assert kept > 0.9 * n and checked > 0.5 * n
+
+
+def test_pyramid_build_on_device():
+    """camera.cpp:63-92 on the GPU: bit-exact against the NumPy restatement (grey levels and f64 edge levels), odd
+    sizes included; and a context created from level 0 only evaluates exactly like one given every level."""
+    from pmvs_b200 import api
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.RandomState(11)
+    for (h, w) in ((389, 613), (480, 640)):
+        img = np.clip(gaussian_filter(rng.rand(h, w), 1.5) * 900 - 320, 0, 255).astype(np.uint8)
+        cfg = abi.readme_config()
+        cfg.maxLOD = 6
+        want = scene.build_pyramid(img, cfg, True)
+        got = api.build_pyramid(img, cfg.lodRatio, cfg.maxLOD, with_edge=True)
+        assert len(got) == len(want) == 7
+        for l, ((g, e), (wg, we)) in enumerate(zip(got, want)):
+            assert g.shape == wg.shape and np.array_equal(g, wg), l
+            assert np.array_equal(e, we), l
+    cfg = abi.readme_config()
+    cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD, cfg.adaptiveGradientEnable = 7, 15, 7 / 3.0, 2, 1
+    sc = scene.SynthScene(cfg, nviews=5, width=400, height=300, seed=3, with_edge=True, tex_size=1024)
+    lean = scene.camera_array(sc.cams)
+    for c in lean:
+        for l in range(c.maxLOD + 1):
+            c.level[l].edge = None
+            if l > 0:
+                c.level[l].grey = None
+    patches = sc.patches(20, seed=2)
+    with PatchRefiner(cfg, sc.records) as a, PatchRefiner(cfg, lean) as b:
+        for lod in (0, 1, 2):
+            hy = scene.hypotheses_from_patches(sc, patches, cfg, lod=lod, seed=lod, per_patch=2)
+            fa, fb = a.fitness(hy), b.fitness(hy)
+            assert fa == fb and any(v != abi.DBL_MAX for v in fa)

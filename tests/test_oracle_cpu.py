@@ -193,3 +193,23 @@ def test_dist_weight_table(small_scene):
     o = orc.Oracle(cfg, sc.records)
     w = np.array(o.dist_weight(cfg.patchSize)).reshape(cfg.patchSize, cfg.patchSize)
     assert abs(w.sum() - 1) < 1e-12 and np.allclose(w, np_reference.dist_table(cfg), rtol=1e-12, atol=0)
+
+
+def test_pyramid_restatement_against_cv2():
+    """INTER_AREA resize and the Sobel(ksize=1) edge image (camera.cpp:71-92) against OpenCV 4.13 where available
+    (same algorithm family as the reference's 2.4.2; +-1 grey level for float rounding)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(5)
+    from scipy.ndimage import gaussian_filter
+    img = np.clip(gaussian_filter(rng.rand(389, 613), 1.5) * 900 - 320, 0, 255).astype(np.uint8)
+    for l in (1, 2, 5):
+        f = 0.8 ** l
+        mine = scene.resize_area(img, f)
+        ref = cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_AREA)
+        assert mine.shape == ref.shape
+        assert np.abs(mine.astype(int) - ref.astype(int)).max() <= 1 and (mine != ref).mean() < 0.01
+    e = scene.edge_image(img)
+    gx = cv2.Sobel(img, cv2.CV_64F, 1, 0, ksize=1)
+    gy = cv2.Sobel(img, cv2.CV_64F, 0, 1, ksize=1)
+    m = np.sqrt(gx * gx + gy * gy)
+    assert np.array_equal(e, (m - m.min()) / (m.max() - m.min()))
