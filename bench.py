@@ -96,6 +96,19 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def traffic_per_launch(args, n):
+    """dram read+write bytes of one refine_kernel launch from the committed ncu capture (profiles/r1_traffic.json),
+    valid only for the launch size it was captured with; --traffic overrides."""
+    if args.traffic is not None:
+        return args.traffic
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p))
+        if t.get("patches") == n:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    return None
+
+
 # ---------------------------------------------------------------------------------------------------------
 def cpu_reference_run(cfg, sc, n_patches, threads, seed=42, first_id=0, patch_seed=5678):
     """The reference's CPU algorithm on host cores: f64 restatement of patch.cpp driven by the UNMODIFIED reference
@@ -269,7 +282,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "refine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": args.traffic,
+                             "frac": achieved / peak, "traffic": traffic_per_launch(args, n),
                              "peak_source": peak_src,
                              "alg_bytes_per_eval": bpe, "window_evals_per_launch": wev_per_launch, "kernel_ms": k_ms,
                              "note": "algorithmic tap-bytes model of SURVEY.md 8(d); the kernel is FP64-pipe bound, see DESIGN.md"}}
