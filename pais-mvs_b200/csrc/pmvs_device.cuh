@@ -905,6 +905,7 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
         __syncthreads();
         ++it;
     }
+    __syncthreads();            /* everyone has read the loop-exit flags */
     if (tid == 0) ps.iteration = it;
     __syncthreads();
     return evals;

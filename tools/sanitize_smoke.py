@@ -1,0 +1,30 @@
+"""Small GPU workload for compute-sanitizer (memcheck / racecheck): fitness + refine (expansion and seed patches, with
+visibility removal) + swarm test + pyramid build on tiny inputs."""
+import os
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "pais-mvs_b200", "python"))
+import numpy as np  # noqa: E402
+from pmvs_b200 import abi, api, scene  # noqa: E402
+from pmvs_b200.api import PatchRefiner  # noqa: E402
+
+cfg = abi.readme_config()
+cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = 4, 9, 4 / 3.0, 1
+cfg.particleNum, cfg.maxIteration, cfg.adaptiveGradientEnable = 6, 4, 1
+sc = scene.SynthScene(cfg, nviews=7, width=160, height=120, seed=5, with_edge=True, tex_size=256, arc_deg=55.0, background=3)
+lean = scene.camera_array(sc.cams)
+for c in lean:
+    for l in range(1, c.maxLOD + 1):
+        c.level[l].grey = None
+        c.level[l].edge = None
+with PatchRefiner(cfg, lean) as pr:
+    ps = sc.patches(6, seed=1, extent=1.6)
+    hy = scene.hypotheses_from_patches(sc, ps, cfg, per_patch=2, spread=2.0)
+    f = pr.fitness(hy)
+    out = pr.refine(ps, flags=abi.F_POST_REMOVE_INVISIBLE | abi.F_EXPAND_VISIBLE)
+    seeds = sc.patches(3, seed=2, ptype=abi.TYPE_SEED)
+    out2 = pr.refine(seeds)
+    r = pr.pso_test([dict(L=[-1, -1, 0], U=[1, 1, 2], init=None, maxIter=5, P=9, fn=0, key=7)])
+pyr = api.build_pyramid(sc.cams[0].levels[0][0], cfg.lodRatio, 2, with_edge=True)
+print("sanitize workload ok", len(f), sum(1 for q in out if not q.drop), sum(1 for q in out2 if not q.drop), r[0]["iterations"], len(pyr))
