@@ -170,6 +170,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = bench_config()
+    if args.particles > 0:
+        cfg.particleNum = args.particles
+    if args.iterations > 0:
+        cfg.maxIteration = args.iterations
     sc = make_scene(cfg, args.views, args.width, args.height)
     V = len(sc.cams)
     n = args.patches
@@ -308,6 +312,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--patches", type=int, default=16384, help="candidate patches per GPU per step")
     ap.add_argument("--views", type=int, default=5)
+    ap.add_argument("--particles", type=int, default=0, help="override particleNum (0 = README config, 15)")
+    ap.add_argument("--iterations", type=int, default=0, help="override maxIteration (0 = README config, 30)")
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--cpu-patches", type=int, default=0, help="CPU sample size (0 = 128 per host core)")

@@ -55,7 +55,7 @@ static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t he
     pl.distOff = off;
     off += sizeof(double) * (size_t)ps * ps;
     pl.warpOff = off;
-    pl.perWarp = (((size_t)vcap * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_COLV_DOUBLES;
+    pl.perWarp = (((size_t)vcap * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_COLV_DOUBLES(vcap);
     off += sizeof(double) * pl.perWarp * nWarps;
     pl.corrOff = off;
     if (withCorr) off += sizeof(double) * (size_t)vcap * vcap;
@@ -84,7 +84,7 @@ __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArg
     W.H = base;
     W.xs = base + (size_t)a.vcap * 9;
     W.ys = W.xs + a.ps;
-    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES;
+    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES(a.vcap);
     return W;
 }
 

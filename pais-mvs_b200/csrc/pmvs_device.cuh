@@ -28,7 +28,8 @@
 #define PMVS_MAX_RADIUS 31
 #define PMVS_MAX_PS (2 * PMVS_MAX_RADIUS + 1)
 #define PMVS_FULL 0xffffffffu
-#define PMVS_COLV_DOUBLES (3 * 5 * 32)
+#define PMVS_COLV_VIEWS(vcap) ((vcap) < 5 ? 5 : ((vcap) > 16 ? 16 : (vcap)))
+#define PMVS_COLV_DOUBLES(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
 
 struct DevLevel {
     const uint32_t *quad;
@@ -69,7 +70,7 @@ struct WarpWork {
     double *H;      /* V*9 */
     double *xs;     /* patchSize */
     double *ys;     /* patchSize */
-    double *colv;   /* PMVS_COLV_DOUBLES: per-lane column constants of the unchecked loop */
+    double *colv;   /* PMVS_COLV_DOUBLES(vcap): per-lane column constants of the unchecked loop */
 };
 
 __device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -387,33 +388,16 @@ __device__ __forceinline__ double quad_bilinear_fast(const uint32_t *__restrict_
 }
 
 /*
- * Unchecked sample loop for exactly VMAX views (compile-time, so every per-view value stays in registers) and windows up
- * to 32 columns: lane = one window column (several row groups when the window is narrow), so the x-dependent part of
- * every homography row, A = H0*x+H2, B = H3*x+H5, C = H6*x+H8, is computed once per evaluation and lives in
- * registers; a sample then costs three fma for the projective coordinates. Two rows are in flight per lane and the
- * body is branch-free (one basic block) for instruction-level parallelism. The reference view (H = I,
- * patch.cpp:317-319) goes through the same arithmetic: A = x, B = y-part 0, w = 1 exactly, so its sample is (x, y)
- * bit-for-bit. Each lane sums its rows in ascending order, then the fixed xor-tree.
+ * Unchecked sample loop for exactly V views (compile-time, 1..16): lane = one window column (several row groups when
+ * the window is narrow, several column passes when it is wider than 32), so the x-dependent part of every homography
+ * row, A = H0*x+H2, B = H3*x+H5, C = H6*x+H8, is computed once per evaluation and parked in a per-lane shared-memory
+ * slot (registers are the scarce resource: the slots buy ptxas room to interleave the per-view chains); a sample then
+ * costs three fma for the projective coordinates. Views are processed in chunks of <= 5, stage by stage across the
+ * chunk (all w, all reciprocal seeds, each refinement step, ...) so neighbouring instructions are independent; the
+ * body is branch-free. The reference view (H = I, patch.cpp:317-319) goes through the same arithmetic: A = x, the
+ * y-part of w is 0 and w = 1 exactly, so its sample is (x, y) bit for bit. Each lane sums its rows in ascending
+ * order, then the fixed xor-tree.
  */
-template <int VMAX>
-struct ColumnViews {
-    double A[VMAX], B[VMAX], C[VMAX];
-};
-
-/*
- * One window row of one column, split in two halves so the caller can put independent work between a tap load and
- * its first use (the L1 round trip is ~40 cycles and there are only ~4 warps per scheduler):
- *   column_coords: projective coordinates of the V views (staged across views: all w, all reciprocal seeds, each
- *                  refinement step, ... so neighbouring instructions are independent), floors, and the V tap loads;
- *   column_blend:  bilinear blend (difference form, see quad_bilinear_fast), cross-view mean and avg-SAD
- *                  (patch.cpp:990-1027).
- */
-template <int VMAX>
-struct ColumnTaps {
-    double fx[VMAX], fy[VMAX];
-    uint32_t q[VMAX];
-};
-
 __device__ __forceinline__ double lds_f64_v(unsigned a) {   /* ordered against the volatile stores below */
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -421,136 +405,183 @@ __device__ __forceinline__ double lds_f64_v(unsigned a) {   /* ordered against t
 }
 __device__ __forceinline__ void sts_f64_v(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 
-/* SM = true: A,B,C live in a per-lane shared-memory slot (cvA + 8*(32*k + lane)) instead of registers */
-template <int VMAX, bool SM>
-__device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, const ColumnViews<VMAX> &cv, unsigned cvA, double y,
-                                              ColumnTaps<VMAX> &t) {
-    double w[VMAX], r[VMAX], e[VMAX];
+template <int N>
+struct ColumnTaps {
+    double fx[N], fy[N];
+    uint32_t q[N];
+};
+
+/* projective coordinates, floors and tap loads of views [v0, v0+N) for the row y of this lane's column;
+ * cvA = this lane's slot base: A,B,C of view v at cvA + 256*(3v + {0,1,2}) */
+template <int N>
+__device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, unsigned cvA, int v0, double y, ColumnTaps<N> &t) {
+    double w[N], r[N], e[N];
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) w[v] = fma(lds_f64(hA + 72u * v + 56u), y, SM ? lds_f64_v(cvA + 256u * (3 * v + 2)) : cv.C[v]);
+    for (int k = 0; k < N; ++k) w[k] = fma(lds_f64(hA + 72u * (v0 + k) + 56u), y, lds_f64_v(cvA + 256u * (3 * (v0 + k) + 2)));
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[v]) : "d"(w[v]));
+    for (int k = 0; k < N; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[k]) : "d"(w[k]));
     /* r = r0*(1 + e + e^2), e = 1 - w*r0: residual e^3 ~ 2^-60 from the ~2^-20 seed, three dependent fma */
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) e[v] = fma(-w[v], r[v], 1.0);
+    for (int k = 0; k < N; ++k) e[k] = fma(-w[k], r[k], 1.0);
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) e[v] = fma(e[v], e[v], e[v]);
+    for (int k = 0; k < N; ++k) e[k] = fma(e[k], e[k], e[k]);
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) r[v] = fma(r[v], e[v], r[v]);
+    for (int k = 0; k < N; ++k) r[k] = fma(r[k], e[k], r[k]);
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        t.fx[v] = fma(lds_f64(hA + 72u * v + 8u), y, SM ? lds_f64_v(cvA + 256u * (3 * v)) : cv.A[v]) * r[v];          /* ix */
-        t.fy[v] = fma(lds_f64(hA + 72u * v + 32u), y, SM ? lds_f64_v(cvA + 256u * (3 * v + 1)) : cv.B[v]) * r[v];     /* iy */
+    for (int k = 0; k < N; ++k) {
+        t.fx[k] = fma(lds_f64(hA + 72u * (v0 + k) + 8u), y, lds_f64_v(cvA + 256u * (3 * (v0 + k)))) * r[k];          /* ix */
+        t.fy[k] = fma(lds_f64(hA + 72u * (v0 + k) + 32u), y, lds_f64_v(cvA + 256u * (3 * (v0 + k) + 1))) * r[k];     /* iy */
     }
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        w[v] = __dadd_rd(t.fx[v], PMVS_MAGIC_FLOOR);
-        r[v] = __dadd_rd(t.fy[v], PMVS_MAGIC_FLOOR);
+    for (int k = 0; k < N; ++k) {
+        w[k] = __dadd_rd(t.fx[k], PMVS_MAGIC_FLOOR);
+        r[k] = __dadd_rd(t.fy[k], PMVS_MAGIC_FLOOR);
     }
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, quad));
-        const int cols = lds_s32(viewA + v * (unsigned)sizeof(ViewS) + (unsigned)offsetof(ViewS, cols));
-        t.q[v] = __ldg(quad + (__double2loint(r[v]) * cols + __double2loint(w[v])));
+    for (int k = 0; k < N; ++k) {
+        const unsigned va = viewA + (unsigned)(v0 + k) * (unsigned)sizeof(ViewS);
+        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(va + (unsigned)offsetof(ViewS, quad));
+        const int cols = lds_s32(va + (unsigned)offsetof(ViewS, cols));
+        t.q[k] = __ldg(quad + (__double2loint(r[k]) * cols + __double2loint(w[k])));
     }
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        t.fx[v] = t.fx[v] - (w[v] - PMVS_MAGIC_FLOOR);
-        t.fy[v] = t.fy[v] - (r[v] - PMVS_MAGIC_FLOOR);
+    for (int k = 0; k < N; ++k) {
+        t.fx[k] = t.fx[k] - (w[k] - PMVS_MAGIC_FLOOR);
+        t.fy[k] = t.fy[k] - (r[k] - PMVS_MAGIC_FLOOR);
     }
 }
 
-template <int VMAX>
-__device__ __forceinline__ double column_blend(const ColumnTaps<VMAX> &t, double invV) {
-    double c[VMAX];
+/* bilinear blend in difference form (see quad_bilinear_fast): byte extraction by PRMT, tap differences in integers,
+ * int->f64 on the (otherwise idle) conversion pipe */
+template <int N>
+__device__ __forceinline__ void column_blend(const ColumnTaps<N> &t, double *c) {
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        /* byte extraction by PRMT, tap differences in integers, int->f64 on the (otherwise idle) conversion pipe */
-        const int g00 = (int)__byte_perm(t.q[v], 0, 0x4440), g01 = (int)__byte_perm(t.q[v], 0, 0x4441);
-        const int g10 = (int)__byte_perm(t.q[v], 0, 0x4442), g11 = (int)__byte_perm(t.q[v], 0, 0x4443);
+    for (int k = 0; k < N; ++k) {
+        const int g00 = (int)__byte_perm(t.q[k], 0, 0x4440), g01 = (int)__byte_perm(t.q[k], 0, 0x4441);
+        const int g10 = (int)__byte_perm(t.q[k], 0, 0x4442), g11 = (int)__byte_perm(t.q[k], 0, 0x4443);
         const int idx = g01 - g00, idy = g10 - g00;
         const double c00 = (double)g00, dx = (double)idx, dy = (double)idy, dxy = (double)(g11 - g10 - idx);
-        c[v] = fma(t.fy[v], fma(t.fx[v], dxy, dy), fma(t.fx[v], dx, c00));
+        c[k] = fma(t.fy[k], fma(t.fx[k], dxy, dy), fma(t.fx[k], dx, c00));
     }
+}
+
+/* cross-view mean and average absolute deviation (patch.cpp:1019-1027) */
+template <int V>
+__device__ __forceinline__ double avg_sad(const double *c, double invV) {
     double mean = 0;
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) mean += c[v];
+    for (int v = 0; v < V; ++v) mean += c[v];
     mean *= invV;
     double sad = 0;
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) sad += fabs(c[v] - mean);
+    for (int v = 0; v < V; ++v) sad += fabs(c[v] - mean);
     return sad * invV;
 }
 
-template <int VMAX, bool SM>
+template <int V, int V0>
+__device__ __forceinline__ void row_chunks(unsigned viewA, unsigned hA, unsigned cvA, double y, double *c) {
+    if constexpr (V0 < V) {
+        constexpr int N = (V - V0) < 4 ? (V - V0) : 4;
+        ColumnTaps<N> t;
+        column_coords<N>(viewA, hA, cvA, V0, y, t);
+        column_blend<N>(t, c + V0);
+        row_chunks<V, V0 + N>(viewA, hA, cvA, y, c);
+    }
+}
+
+template <int V>
 __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
                                              const double *__restrict__ Hw, const double *__restrict__ xs,
                                              const double *__restrict__ ys, double *colv, int nx, int ny, double &fitOut, double &swOut) {
     const int lane = threadIdx.x & 31;
-    const int G = 32 / nx;                         /* row groups sharing the warp */
-    const int i = lane % nx, g = lane / nx;
-    const bool active = g < G;
-    const unsigned hA = smem_addr(Hw), ysA = smem_addr(ys), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
-    const double x = lds_f64(smem_addr(xs) + 8u * i);
-    const double invV = 1.0 / (double)VMAX;
+    const int G = nx <= 16 ? 32 / nx : 1;          /* row groups sharing the warp (narrow windows) */
+    const unsigned hA = smem_addr(Hw), ysA = smem_addr(ys), xsA = smem_addr(xs), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
+    const unsigned cvA = smem_addr(colv) + 8u * lane;
+    const double invV = 1.0 / (double)V;
     const bool useDist = S.cfg.adaptiveDistanceEnable, useDiff = S.cfg.adaptiveDifferenceEnable, useGrad = S.cfg.adaptiveGradientEnable;
     const double invDiffW = 1.0 / S.cfg.diffWeighting, gradW = S.cfg.gradientWeighting;
-    ColumnViews<VMAX> cv;
-    const unsigned cvA = smem_addr(colv) + 8u * lane;
-#pragma unroll
-    for (int v = 0; v < VMAX; ++v) {
-        const unsigned h = hA + 72u * v;
-        const double a = fma(lds_f64(h), x, lds_f64(h + 16u)), b = fma(lds_f64(h + 24u), x, lds_f64(h + 40u));
-        const double c = fma(lds_f64(h + 48u), x, lds_f64(h + 64u));
-        if (SM) {
-            sts_f64_v(cvA + 256u * (3 * v), a);
-            sts_f64_v(cvA + 256u * (3 * v + 1), b);
-            sts_f64_v(cvA + 256u * (3 * v + 2), c);
-            cv.A[v] = cv.B[v] = cv.C[v] = 0;
-        } else {
-            cv.A[v] = a;
-            cv.B[v] = b;
-            cv.C[v] = c;
-        }
-    }
-    const int rx = __double2int_rn(x);
     const uint32_t *__restrict__ refQuad = E.refQuad;
     const double *__restrict__ refEdge = E.refEdge;
     const int refCols = E.refCols;
     double fit = 0, sw = 0;
-    const int jEnd = active ? ny : 0;
-    for (int j = g; j < jEnd; j += 2 * G) {
-        const bool two = j + G < jEnd;
-        const int j2 = two ? j + G : j;
-        const double y0 = lds_f64(ysA + 8u * j), y1 = lds_f64(ysA + 8u * j2);
-        const int rofs0 = __double2int_rn(y0) * refCols + rx, rofs1 = __double2int_rn(y1) * refCols + rx;
-        const bool keep0 = (__ldg(refQuad + rofs0) & 0xffu) != 0;                       /* patch.cpp:986 */
-        const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
-        /* both rows' tap loads are in flight before the first one is consumed */
-        ColumnTaps<VMAX> ta, tb;
-        column_coords<VMAX, SM>(viewA, hA, cv, cvA, y0, ta);
-        column_coords<VMAX, SM>(viewA, hA, cv, cvA, y1, tb);
-        const double s0 = column_blend<VMAX>(ta, invV);
-        const double s1 = column_blend<VMAX>(tb, invV);
-        double w0 = 1.0, w1 = 1.0;
-        if (useDist) {                                                                    /* patch.cpp:1030-1032 */
-            w0 = lds_f64(distA + 8u * (i * ny + j));
-            w1 = lds_f64(distA + 8u * (i * ny + j2));
+    for (int i0 = 0; i0 < nx; i0 += 32) {          /* column passes (windows wider than the warp) */
+        const int span = nx - i0 < 32 ? nx - i0 : 32;
+        const int i = i0 + (G > 1 ? lane % nx : lane), g = G > 1 ? lane / nx : 0;
+        const bool active = G > 1 ? g < G : lane < span;
+        const double x = lds_f64(xsA + 8u * (active ? i : i0));
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const unsigned h = hA + 72u * v;
+            sts_f64_v(cvA + 256u * (3 * v), fma(lds_f64(h), x, lds_f64(h + 16u)));
+            sts_f64_v(cvA + 256u * (3 * v + 1), fma(lds_f64(h + 24u), x, lds_f64(h + 40u)));
+            sts_f64_v(cvA + 256u * (3 * v + 2), fma(lds_f64(h + 48u), x, lds_f64(h + 64u)));
         }
-        if (useDiff) { w0 *= exp_nonpos(-s0 * s0 * invDiffW); w1 *= exp_nonpos(-s1 * s1 * invDiffW); }    /* patch.cpp:1033-1035 */
-        if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
-            w0 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs0) * gradW));
-            w1 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs1) * gradW));
+        const int rx = __double2int_rn(x);
+        const int jEnd = active ? ny : 0;
+        for (int j = g; j < jEnd; j += 2 * G) {
+            const bool two = j + G < jEnd;
+            const int j2 = two ? j + G : j;
+            const double y0 = lds_f64(ysA + 8u * j), y1 = lds_f64(ysA + 8u * j2);
+            const int rofs0 = __double2int_rn(y0) * refCols + rx, rofs1 = __double2int_rn(y1) * refCols + rx;
+            const bool keep0 = (__ldg(refQuad + rofs0) & 0xffu) != 0;                       /* patch.cpp:986 */
+            const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
+            double s0, s1;
+            if constexpr (V <= 5) {
+                /* both rows' tap loads are in flight before the first one is consumed */
+                ColumnTaps<V> ta, tb;
+                double ca[V], cb[V];
+                column_coords<V>(viewA, hA, cvA, 0, y0, ta);
+                column_coords<V>(viewA, hA, cvA, 0, y1, tb);
+                column_blend<V>(ta, ca);
+                column_blend<V>(tb, cb);
+                s0 = avg_sad<V>(ca, invV);
+                s1 = avg_sad<V>(cb, invV);
+            } else {
+                /* many views: one row at a time (a real loop, so the two rows' colours are never live together) */
+                s0 = s1 = 0;
+#pragma unroll 1
+                for (int rrow = 0; rrow < 2; ++rrow) {
+                    double c[V];
+                    row_chunks<V, 0>(viewA, hA, cvA, rrow ? y1 : y0, c);
+                    const double sv = avg_sad<V>(c, invV);
+                    if (rrow) s1 = sv;
+                    else s0 = sv;
+                }
+            }
+            double w0 = 1.0, w1 = 1.0;
+            if (useDist) {                                                                    /* patch.cpp:1030-1032 */
+                w0 = lds_f64(distA + 8u * (i * ny + j));
+                w1 = lds_f64(distA + 8u * (i * ny + j2));
+            }
+            if (useDiff) { w0 *= exp_nonpos(-s0 * s0 * invDiffW); w1 *= exp_nonpos(-s1 * s1 * invDiffW); }    /* patch.cpp:1033-1035 */
+            if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
+                w0 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs0) * gradW));
+                w1 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs1) * gradW));
+            }
+            w0 = keep0 ? w0 : 0.0;
+            w1 = keep1 ? w1 : 0.0;
+            sw += w0;
+            fit = fma(w0, s0, fit);
+            sw += w1;
+            fit = fma(w1, s1, fit);
         }
-        w0 = keep0 ? w0 : 0.0;
-        w1 = keep1 ? w1 : 0.0;
-        sw += w0;
-        fit = fma(w0, s0, fit);
-        sw += w1;
-        fit = fma(w1, s1, fit);
     }
     fitOut = warp_sum(fit);
     swOut = warp_sum(sw);
+}
+
+template <int V>
+__device__ __forceinline__ bool fitness_columns_dispatch(int nV, const DevScene &S, const EvalCtx &E, const double *sDistW,
+                                                         const WarpWork &W, int nx, int ny, double &fit, double &sw) {
+    if constexpr (V >= 1) {
+        if (nV == V) {
+            fitness_columns<V>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
+            return true;
+        }
+        return fitness_columns_dispatch<V - 1>(nV, S, E, sDistW, W, nx, ny, fit, sw);
+    } else {
+        return false;
+    }
 }
 
 /*
@@ -602,11 +633,9 @@ __device__ __noinline__ double warp_fitness(const DevScene &S, const EvalCtx &E,
     bool ok;
     if (inside) {
         ok = true;
-        if (VCAP == 8 && E.V == 5 && nx <= 32 && nx > 0) {
-            if (S.tune & 1) fitness_columns<5, true>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
-            else fitness_columns<5, false>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
-        } else if (VCAP == 8 && E.V == 4 && nx <= 32 && nx > 0) fitness_columns<4, false>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
-        else if (VCAP == 8 && E.V == 3 && nx <= 32 && nx > 0) fitness_columns<3, false>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
+        /* lane-per-column loop: every V in 1..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
+        if (VCAP == 8 && nx > 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, W, nx, ny, fit, sw)) {}
+        else if (VCAP == 16 && nx > 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, W, nx, ny, fit, sw)) {}
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     __syncwarp();

@@ -142,9 +142,12 @@ def test_fitness_golden(small_scene):
 
 
 @pytest.mark.parametrize("nviews,radius,weights", [(5, 7, (0, 0, 0)), (5, 15, (1, 1, 0)), (3, 4, (1, 1, 1)), (12, 7, (1, 1, 1)),
-                                                   (20, 5, (1, 1, 0)), (40, 3, (1, 0, 1))])
+                                                   (20, 5, (1, 1, 0)), (40, 3, (1, 0, 1)), (1, 6, (1, 1, 0)), (2, 6, (1, 1, 1)),
+                                                   (6, 5, (1, 1, 0)), (7, 9, (0, 1, 1)), (8, 17, (1, 1, 0)), (9, 9, (1, 0, 0)),
+                                                   (16, 21, (1, 1, 1)), (4, 21, (1, 1, 0))])
 def test_fitness_vs_oracle(nviews, radius, weights):
-    """V <= 8 / <= 16 register paths and the V > 16 two-pass path; borders (DBL_MAX), masked pixels, all LODs."""
+    """Every lane-per-column instantiation family (V = 1..16, narrow windows with row groups, windows wider than a warp),
+    the generic V > 16 two-pass path and the checked path; borders (DBL_MAX), masked pixels, all LODs."""
     cfg = abi.readme_config()
     cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = radius, 2 * radius + 1, radius / 3.0, 2
     cfg.adaptiveDistanceEnable, cfg.adaptiveDifferenceEnable, cfg.adaptiveGradientEnable = weights
