@@ -13,7 +13,9 @@
 #define TMVS_HOST_H
 
 #include <cstdint>
+#include <deque>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -78,7 +80,7 @@ public:
     std::map<int, Patch> patches;
     std::vector<Patch> deletedPatches;
     std::vector<CellMap> cellMaps;
-    std::vector<int> queue;
+    std::vector<int> queue;            /* insertion order (the reference's container) */
     int nextId = 0;
     int roundSize = 256;               /* parents popped per expansion round */
     int device = 0;
@@ -109,10 +111,16 @@ public:
     void getExpansionPatchCenter(const Camera &cam, const Patch &parent, int cx, int cy, double center[3]) const;   /* mvs.cpp:809-836 */
     bool skipNeighborCell(const std::vector<int> &cell, const Patch &ref) const;                                    /* mvs.cpp:792-807 */
     static bool isNeighbor(const Patch &a, const Patch &b, double neighborRadius);                                  /* patch.cpp:6-23 */
-    int getPatchIdFromQueue();                                      /* mvs.cpp:656-788 */
+    int getPatchIdFromQueue();                                      /* mvs.cpp:636-788, indexed */
+    size_t byPriorityQueueSize() const { return prioQueue.size() > fifo.size() ? prioQueue.size() : fifo.size(); }
     const std::string &lastError() const { return err; }
 
 private:
+    std::set<std::pair<std::pair<double, long>, int> > prioQueue;
+    std::deque<int> fifo;
+    long queueSeq = 0;
+    void queuePush(int id);
+    void queueClear();
     pmvs_ctx *ctx = nullptr;
     std::string err;
     bool ensureContext();

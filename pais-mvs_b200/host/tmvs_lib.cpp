@@ -445,7 +445,7 @@ void MVS::setCellMaps() {   /* mvs.cpp:116-133 (+ initCellMaps :74-88) */
 void MVS::insertPatch(const Patch &p) {   /* mvs.cpp:579-601 */
     if (!runtimeFiltering(p)) return;
     patches.insert(std::pair<int, Patch>(p.id, p));
-    queue.push_back(p.id);
+    queuePush(p.id);
     for (size_t i = 0; i < p.camIdx.size() && 2 * i + 1 < p.imgPoint.size(); ++i)
         cellMaps[p.camIdx[i]].insert((int)(p.imgPoint[2 * i] / cfg.cellSize), (int)(p.imgPoint[2 * i + 1] / cfg.cellSize), p.id);
 }
@@ -462,46 +462,45 @@ void MVS::deletePatch(int id) {   /* mvs.cpp:607-634 */
     patches.erase(it);
 }
 
-int MVS::getPatchIdFromQueue() {   /* mvs.cpp:636-788 */
-    /* entries whose patch is gone or already expanded are erased while scanning, as in the reference */
-    std::vector<int> live;
-    live.reserve(queue.size());
-    for (size_t k = 0; k < queue.size(); ++k) {
-        std::map<int, Patch>::const_iterator it = patches.find(queue[k]);
+/* The reference scans the whole queue for every pop (mvs.cpp:656-788), which is quadratic in the number of patches and
+ * would dominate once refine() runs on the GPU. Same selection rule, indexed: best/worst-first keep the live entries
+ * ordered by (priority, insertion sequence) — the reference's strict comparison picks the earliest-inserted among equal
+ * priorities — breadth/depth-first pop from the two ends. Entries whose patch is gone or already expanded are dropped
+ * lazily when they surface, like the reference erases them while scanning. */
+void MVS::queuePush(int id) {
+    queue.push_back(id);
+    std::map<int, Patch>::const_iterator it = patches.find(id);
+    const double pr = it == patches.end() ? 0.0 : it->second.priority;
+    const double key = cfg.expansionStrategy == EXPANSION_WORST_FIRST ? -pr : pr;
+    if (!std::isnan(key) && pr < DBL_MAX) prioQueue.insert(std::make_pair(std::make_pair(key, queueSeq), id));   /* NaN / DBL_MAX are never selected (:682, :717) */
+    fifo.push_back(id);
+    ++queueSeq;
+}
+
+void MVS::queueClear() {
+    queue.clear();
+    prioQueue.clear();
+    fifo.clear();
+    queueSeq = 0;
+}
+
+int MVS::getPatchIdFromQueue() {
+    const bool byPriority = cfg.expansionStrategy != EXPANSION_BREATH_FIRST && cfg.expansionStrategy != EXPANSION_DEPTH_FIRST;
+    for (;;) {
+        int id;
+        if (byPriority) {
+            if (prioQueue.empty()) return -1;
+            id = prioQueue.begin()->second;
+            prioQueue.erase(prioQueue.begin());
+        } else {
+            if (fifo.empty()) return -1;
+            if (cfg.expansionStrategy == EXPANSION_BREATH_FIRST) { id = fifo.front(); fifo.pop_front(); }
+            else { id = fifo.back(); fifo.pop_back(); }
+        }
+        std::map<int, Patch>::const_iterator it = patches.find(id);
         if (it == patches.end() || it->second.expanded) continue;
-        live.push_back(queue[k]);
+        return id;
     }
-    queue.swap(live);
-    if (queue.empty()) return -1;
-    size_t pick = 0;
-    switch (cfg.expansionStrategy) {
-    default:
-    case EXPANSION_BEST_FIRST: {
-        double top = DBL_MAX;
-        bool found = false;
-        for (size_t k = 0; k < queue.size(); ++k) {
-            const double pr = patches.find(queue[k])->second.priority;
-            if (pr < top) { top = pr; pick = k; found = true; }
-        }
-        if (!found) return -1;      /* every priority is DBL_MAX/NaN: the reference returns -1 and keeps scanning an idle queue */
-        break;
-    }
-    case EXPANSION_WORST_FIRST: {
-        double top = -DBL_MAX;
-        bool found = false;
-        for (size_t k = 0; k < queue.size(); ++k) {
-            const double pr = patches.find(queue[k])->second.priority;
-            if (pr > top) { top = pr; pick = k; found = true; }
-        }
-        if (!found) return -1;
-        break;
-    }
-    case EXPANSION_BREATH_FIRST: pick = 0; break;
-    case EXPANSION_DEPTH_FIRST: pick = queue.size() - 1; break;
-    }
-    const int id = queue[pick];
-    queue.erase(queue.begin() + (long)pick);
-    return id;
 }
 
 /* --- GPU ------------------------------------------------------------------------------------------------ */
@@ -620,8 +619,8 @@ bool MVS::refineSeedPatches() {   /* mvs.cpp:196-231 */
 
 bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     setCellMaps();
-    queue.clear();
-    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) queue.push_back(it->first);
+    queueClear();                                  /* initPriorityQueue, mvs.cpp:90-95 */
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) queuePush(it->first);
     setNeighborRadius();
     if (!ensureContext()) return false;
     size_t saveTime = 0;
@@ -683,7 +682,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
         }
         if (verbose)
             printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), cands.size(), accepted,
-                   patches.size(), queue.size());
+                   patches.size(), byPriorityQueueSize());
         if (patches.size() / 500 > saveTime) {   /* mvs.cpp:265-268 */
             saveTime = patches.size() / 500;
             writeMVS("auto_save.mvs");

@@ -1,0 +1,29 @@
+"""End-to-end timing of `tmvs -r` on a synthetic NVM scene: how much of the wall clock is GPU refinement vs the host's
+serial commit (the expected scaling limit). usage: python tools/tmvs_scale.py [width height round cell]"""
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "pais-mvs_b200", "python"))
+from pmvs_b200 import abi, mvsio, scene  # noqa: E402
+
+w = int(sys.argv[1]) if len(sys.argv) > 1 else 800
+h = int(sys.argv[2]) if len(sys.argv) > 2 else 600
+rnd = sys.argv[3] if len(sys.argv) > 3 else "512"
+cell = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+cfg = abi.readme_config()
+cfg.maxLOD = 2
+cfg.cellSize = cell
+sc = scene.SynthScene(cfg, nviews=5, width=w, height=h, seed=1234)
+with tempfile.TemporaryDirectory() as d:
+    path = mvsio.write_nvm_scene(d, sc, n_seeds=64)
+    mvsio.write_config(os.path.join(d, "config.txt"), cfg)
+    t0 = time.time()
+    r = subprocess.run([os.path.join(ROOT, "pais-mvs_b200", "bin", "tmvs"), "-r", path, "--config", os.path.join(d, "config.txt"),
+                        "--out-dir", d, "--round", rnd], cwd=d, capture_output=True, text=True)
+    dt = time.time() - t0
+    print(r.stdout[-600:], r.stderr[-400:])
+    print("wall %.2f s (incl. image load + pyramid build)" % dt)
