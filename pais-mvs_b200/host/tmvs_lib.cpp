@@ -638,20 +638,36 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             parents.push_back(id);
         }
         if (parents.empty()) break;
-        /* 2. candidates of every parent (expandNeighborCell mvs.cpp:529-564) */
-        std::vector<Cand> cands;
-        std::vector<Patch> cpatch;
-        std::vector<std::vector<int> > parentCams;
-        for (size_t k = 0; k < parents.size(); ++k) {
-            const Patch &pth = patches.find(parents[k])->second;
-            for (size_t i = 0; i < pth.camIdx.size() && 2 * i + 1 < pth.imgPoint.size(); ++i) {
-                const int ci = pth.camIdx[i];
+        /* 2.-4. The reference visits a parent's visible cameras one after the other (expandNeighborCell,
+         * mvs.cpp:535-563) and inserts each refined candidate before looking at the next camera, so the (up to) five
+         * views of the same 3-D neighbour are refined once: the first one fills the cells the others would target.
+         * A round therefore runs one pass per camera slot i: candidates of slot i for all parents -> GPU -> serial
+         * commit in parent order -> slot i+1 sees the updated cell maps. */
+        size_t nCands = 0, accepted = 0;
+        for (size_t slot = 0;; ++slot) {
+            std::vector<Cand> cands;
+            std::vector<Patch> cpatch;
+            std::vector<std::vector<int> > parentCams;
+            /* a cell can take at most maxCellPatchNum patches (skipNeighborCell, mvs.cpp:794-795): do not refine more
+             * candidates for a cell than it still has room for — the serial reference would have skipped them */
+            std::map<std::pair<int, std::pair<int, int> >, int> pending;
+            bool anySlot = false;
+            for (size_t k = 0; k < parents.size(); ++k) {
+                std::map<int, Patch>::const_iterator pit = patches.find(parents[k]);
+                if (pit == patches.end()) continue;
+                const Patch &pth = pit->second;
+                if (slot >= pth.camIdx.size() || 2 * slot + 1 >= pth.imgPoint.size()) continue;
+                anySlot = true;
+                const int ci = pth.camIdx[slot];
                 const CellMap &m = cellMaps[ci];
-                const int cx = (int)(pth.imgPoint[2 * i] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * i + 1] / cfg.cellSize);
+                const int cx = (int)(pth.imgPoint[2 * slot] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * slot + 1] / cfg.cellSize);
                 const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
                 for (int j = 0; j < 4; ++j) {
                     if (!m.inMap(nx[j], ny[j])) continue;
                     if (skipNeighborCell(m.cell(nx[j], ny[j]), pth)) continue;
+                    int &pend = pending[std::make_pair(ci, std::make_pair(nx[j], ny[j]))];
+                    if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
+                    ++pend;
                     Patch e;                                   /* Patch(center, parent), patch.cpp:36-43 */
                     e.type = PMVS_TYPE_EXPAND;
                     e.id = nextId++;
@@ -664,24 +680,25 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                     parentCams.push_back(pth.camIdx);
                 }
             }
-        }
-        /* 3. refine the whole round on the GPU (expandVisibleCamera + refine + removeInvisibleCamera, mvs.cpp:572-574) */
-        std::vector<Patch *> batch(cpatch.size());
-        for (size_t k = 0; k < cpatch.size(); ++k) batch[k] = &cpatch[k];
-        if (!refineBatch(batch, PMVS_F_EXPAND_VISIBLE | PMVS_F_POST_REMOVE_INVISIBLE, &parentCams)) return false;
-        /* 4. commit serially in parent order; a cell another candidate of this round filled in the meantime is
-         *    re-checked exactly like the reference would have seen it (skipNeighborCell + insertPatch) */
-        size_t accepted = 0;
-        for (size_t k = 0; k < cands.size(); ++k) {
-            std::map<int, Patch>::const_iterator pit = patches.find(cands[k].parent);
-            if (pit == patches.end()) continue;
-            if (skipNeighborCell(cellMaps[cands[k].cam].cell(cands[k].cx, cands[k].cy), pit->second)) continue;
-            const size_t before = patches.size();
-            insertPatch(cpatch[k]);
-            accepted += patches.size() - before;
+            if (!anySlot) break;
+            if (cands.empty()) continue;
+            /* expandVisibleCamera + refine + removeInvisibleCamera on the GPU (mvs.cpp:572-574) */
+            std::vector<Patch *> batch(cpatch.size());
+            for (size_t k = 0; k < cpatch.size(); ++k) batch[k] = &cpatch[k];
+            if (!refineBatch(batch, PMVS_F_EXPAND_VISIBLE | PMVS_F_POST_REMOVE_INVISIBLE, &parentCams)) return false;
+            /* serial commit in parent order; the target cell is re-checked as the reference would have seen it */
+            for (size_t k = 0; k < cands.size(); ++k) {
+                std::map<int, Patch>::const_iterator pit = patches.find(cands[k].parent);
+                if (pit == patches.end()) continue;
+                if (skipNeighborCell(cellMaps[cands[k].cam].cell(cands[k].cx, cands[k].cy), pit->second)) continue;
+                const size_t before = patches.size();
+                insertPatch(cpatch[k]);
+                accepted += patches.size() - before;
+            }
+            nCands += cands.size();
         }
         if (verbose)
-            printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), cands.size(), accepted,
+            printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), nCands, accepted,
                    patches.size(), byPriorityQueueSize());
         if (patches.size() / 500 > saveTime) {   /* mvs.cpp:265-268 */
             saveTime = patches.size() / 500;
