@@ -5,7 +5,8 @@
  * -v / -a viewer) are outside this repository's scope.
  *
  * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
- * round), --device D, --seed S (run seed of the counter-based PSO RNG), --no-expand, -V (verbose),
+ * round, default 1024), --device D, --gpus N (shard every batch over N GPUs), --seed S (run seed of the counter-based PSO
+ * RNG), --no-expand, -V (verbose),
  * --convert IN OUT.mvs (load + write only: needs no GPU).
  */
 #include <chrono>
@@ -30,7 +31,7 @@ static bool loadAny(MVS &mvs, const std::string &file) {
 
 int main(int argc, char **argv) {
     std::string mode, input, configFile = "config.txt", outDir, imageDir, convertOut;
-    int roundSize = 256, device = 0;
+    int roundSize = 1024, device = 0, gpus = 1;
     unsigned long long seed = 42;
     bool expand = true, verbose = false;
     for (int i = 1; i < argc; ++i) {
@@ -42,13 +43,14 @@ int main(int argc, char **argv) {
         else if (a == "--image-dir" && i + 1 < argc) imageDir = argv[++i];
         else if (a == "--round" && i + 1 < argc) roundSize = atoi(argv[++i]);
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
+        else if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
         else if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
         else if (a == "--no-expand") expand = false;
         else if (a == "-V") verbose = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     if (mode.empty()) {   /* TMVS.cpp:183-197 */
-        printf("usage: tmvs -r <input.nvm|input.nvm2|input.mvs> [--config config.txt] [--out-dir DIR] [--round K] [--device D] [--seed S]\n");
+        printf("usage: tmvs -r <input.nvm|input.nvm2|input.mvs> [--config config.txt] [--out-dir DIR] [--round K] [--device D] [--gpus N] [--seed S]\n");
         return 2;
     }
     if (mode == "-f" || mode == "-v" || mode == "-a") {
@@ -64,6 +66,7 @@ int main(int argc, char **argv) {
     MVS mvs(config);                                         /* TMVS.cpp:181 */
     mvs.roundSize = roundSize > 0 ? roundSize : 1;
     mvs.device = device;
+    mvs.numGpus = gpus > 0 ? gpus : 1;
     mvs.rngSeed = seed;
     mvs.verbose = verbose;
     mvs.imageDir = imageDir;

@@ -82,8 +82,9 @@ public:
     std::vector<CellMap> cellMaps;
     std::vector<int> queue;            /* insertion order (the reference's container) */
     int nextId = 0;
-    int roundSize = 256;               /* parents popped per expansion round */
-    int device = 0;
+    int roundSize = 1024;              /* parents popped per expansion round */
+    int device = 0;                    /* first device */
+    int numGpus = 1;                   /* devices device .. device+numGpus-1, candidates sharded by index */
     uint64_t rngSeed = 42;
     bool verbose = false;
     std::string imageDir;              /* prefix for camera image files */
@@ -121,7 +122,7 @@ private:
     long queueSeq = 0;
     void queuePush(int id);
     void queueClear();
-    pmvs_ctx *ctx = nullptr;
+    std::vector<pmvs_ctx *> ctxs;       /* one per GPU */
     std::string err;
     bool ensureContext();
     void setCellMaps();                                             /* mvs.cpp:116-133 */

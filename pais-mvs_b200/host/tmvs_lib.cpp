@@ -14,6 +14,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 namespace tmvs {
 
@@ -240,7 +241,8 @@ MVS::MVS(const MvsConfig &c) {
     setConfig(c);
 }
 MVS::~MVS() {
-    if (ctx) pmvs_destroy(ctx);
+    for (size_t g = 0; g < ctxs.size(); ++g)
+        if (ctxs[g]) pmvs_destroy(ctxs[g]);
 }
 
 void MVS::setConfig(const MvsConfig &c) {   /* mvs.cpp:42-72: neighborRadius is NOT copied (derived at run time) */
@@ -248,9 +250,9 @@ void MVS::setConfig(const MvsConfig &c) {   /* mvs.cpp:42-72: neighborRadius is 
     cfg = c;
     cfg.patchSize = (cfg.patchRadius << 1) + 1;
     cfg.neighborRadius = keep;
-    if (ctx) {
-        if (pmvs_set_config(ctx, &cfg) != PMVS_OK) err = pmvs_last_error(ctx);
-        pmvs_set_neighbor_radius(ctx, cfg.neighborRadius);
+    for (size_t g = 0; g < ctxs.size(); ++g) {
+        if (pmvs_set_config(ctxs[g], &cfg) != PMVS_OK) err = pmvs_last_error(ctxs[g]);
+        pmvs_set_neighbor_radius(ctxs[g], cfg.neighborRadius);
     }
 }
 
@@ -354,7 +356,7 @@ void MVS::setNeighborRadius() {   /* mvs.cpp:147-152 + getBoundingVolume :967-99
         }
     const double volume = fabs((mx[0] - mn[0]) * (mx[1] - mn[1]) * (mx[2] - mn[2]));
     cfg.neighborRadius = pow(volume, 1.0 / 3.0) * cfg.neighborRadiusScalar;
-    if (ctx) pmvs_set_neighbor_radius(ctx, cfg.neighborRadius);
+    for (size_t g = 0; g < ctxs.size(); ++g) pmvs_set_neighbor_radius(ctxs[g], cfg.neighborRadius);
     if (verbose) printf("neighborRadius %f\n", cfg.neighborRadius);
 }
 
@@ -504,8 +506,9 @@ int MVS::getPatchIdFromQueue() {
 }
 
 /* --- GPU ------------------------------------------------------------------------------------------------ */
+/* one context per GPU: the scene (cameras, pyramids, tables) is replicated, patches are sharded */
 bool MVS::ensureContext() {
-    if (ctx) return true;
+    if (!ctxs.empty()) return true;
     std::vector<PmvsCamera> recs(cameras.size());
     for (size_t i = 0; i < cameras.size(); ++i) {
         const Camera &c = cameras[i];
@@ -528,12 +531,17 @@ bool MVS::ensureContext() {
             r.level[l].edge = nullptr;
         }
     }
-    const int rc = pmvs_create(&ctx, &cfg, (int)recs.size(), recs.data(), device, rngSeed);
-    if (rc != PMVS_OK) {
-        err = std::string("pmvs_create: ") + (ctx ? pmvs_last_error(ctx) : "out of memory");
-        if (ctx) pmvs_destroy(ctx);
-        ctx = nullptr;
-        return false;
+    for (int g = 0; g < (numGpus > 0 ? numGpus : 1); ++g) {
+        pmvs_ctx *c = nullptr;
+        const int rc = pmvs_create(&c, &cfg, (int)recs.size(), recs.data(), device + g, rngSeed);
+        if (rc != PMVS_OK) {
+            err = std::string("pmvs_create (device ") + std::to_string(device + g) + "): " + (c ? pmvs_last_error(c) : "out of memory");
+            if (c) pmvs_destroy(c);
+            for (size_t k = 0; k < ctxs.size(); ++k) pmvs_destroy(ctxs[k]);
+            ctxs.clear();
+            return false;
+        }
+        ctxs.push_back(c);
     }
     return true;
 }
@@ -572,9 +580,21 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
         for (int k = 0; k < r.nCam; ++k) r.camIdx[k] = (uint16_t)cams[k];
     }
     const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    const int rc = pmvs_refine_batch(ctx, n, in.data(), out.data(), flags);
+    /* contiguous shards, one host thread per GPU; results do not depend on the split (the PSO stream is keyed by patch id) */
+    const int G = (int)ctxs.size();
+    std::vector<int> rcs(G, PMVS_OK);
+    if (G == 1 || n < 2 * G) rcs[0] = pmvs_refine_batch(ctxs[0], n, in.data(), out.data(), flags);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) {
+            const int lo = (int)((long)n * g / G), hi = (int)((long)n * (g + 1) / G);
+            th.push_back(std::thread([&, g, lo, hi]() { rcs[g] = pmvs_refine_batch(ctxs[g], hi - lo, in.data() + lo, out.data() + lo, flags); }));
+        }
+        for (int g = 0; g < G; ++g) th[g].join();
+    }
     gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc != PMVS_OK) { err = std::string("pmvs_refine_batch: ") + pmvs_last_error(ctx); return false; }
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != PMVS_OK) { err = std::string("pmvs_refine_batch: ") + pmvs_last_error(ctxs[g]); return false; }
     refinedCount += n;
     for (int i = 0; i < n; ++i) {
         Patch &p = *batch[i];
@@ -607,7 +627,7 @@ bool MVS::refineSeedPatches() {   /* mvs.cpp:196-231 */
     }
     for (size_t k = 0; k < few.size(); ++k) deletePatch(few[k]);
     if (!ensureContext()) return false;
-    pmvs_set_neighbor_radius(ctx, cfg.neighborRadius);
+    for (size_t g = 0; g < ctxs.size(); ++g) pmvs_set_neighbor_radius(ctxs[g], cfg.neighborRadius);
     if (!refineBatch(batch, PMVS_F_POST_REMOVE_INVISIBLE, nullptr)) return false;
     std::vector<int> bad;
     for (std::map<int, Patch>::iterator it = patches.begin(); it != patches.end(); ++it)
@@ -625,8 +645,12 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     if (!ensureContext()) return false;
     size_t saveTime = 0;
     struct Cand { int parent, cam, cx, cy; };
+    typedef std::chrono::steady_clock Clock;
+    double tPop = 0, tGen = 0, tCommit = 0, tSave = 0;
+    long gpuCalls = 0;
     for (int round = 0;; ++round) {
         /* 1. pop up to roundSize parents in strategy order */
+        Clock::time_point tp0 = Clock::now();
         std::vector<int> parents;
         while ((int)parents.size() < roundSize) {
             const int id = getPatchIdFromQueue();
@@ -637,6 +661,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             if (!runtimeFiltering(it->second)) { deletePatch(id); continue; }   /* mvs.cpp:255-260 */
             parents.push_back(id);
         }
+        tPop += std::chrono::duration<double>(Clock::now() - tp0).count();
         if (parents.empty()) break;
         /* 2.-4. The reference visits a parent's visible cameras one after the other (expandNeighborCell,
          * mvs.cpp:535-563) and inserts each refined candidate before looking at the next camera, so the (up to) five
@@ -645,6 +670,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
          * commit in parent order -> slot i+1 sees the updated cell maps. */
         size_t nCands = 0, accepted = 0;
         for (size_t slot = 0;; ++slot) {
+            Clock::time_point tg0 = Clock::now();
             std::vector<Cand> cands;
             std::vector<Patch> cpatch;
             std::vector<std::vector<int> > parentCams;
@@ -680,13 +706,16 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                     parentCams.push_back(pth.camIdx);
                 }
             }
+            tGen += std::chrono::duration<double>(Clock::now() - tg0).count();
             if (!anySlot) break;
             if (cands.empty()) continue;
+            ++gpuCalls;
             /* expandVisibleCamera + refine + removeInvisibleCamera on the GPU (mvs.cpp:572-574) */
             std::vector<Patch *> batch(cpatch.size());
             for (size_t k = 0; k < cpatch.size(); ++k) batch[k] = &cpatch[k];
             if (!refineBatch(batch, PMVS_F_EXPAND_VISIBLE | PMVS_F_POST_REMOVE_INVISIBLE, &parentCams)) return false;
             /* serial commit in parent order; the target cell is re-checked as the reference would have seen it */
+            Clock::time_point tc0 = Clock::now();
             for (size_t k = 0; k < cands.size(); ++k) {
                 std::map<int, Patch>::const_iterator pit = patches.find(cands[k].parent);
                 if (pit == patches.end()) continue;
@@ -696,15 +725,19 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 accepted += patches.size() - before;
             }
             nCands += cands.size();
+            tCommit += std::chrono::duration<double>(Clock::now() - tc0).count();
         }
         if (verbose)
             printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), nCands, accepted,
                    patches.size(), byPriorityQueueSize());
         if (patches.size() / 500 > saveTime) {   /* mvs.cpp:265-268 */
+            Clock::time_point ts0 = Clock::now();
             saveTime = patches.size() / 500;
             writeMVS("auto_save.mvs");
+            tSave += std::chrono::duration<double>(Clock::now() - ts0).count();
         }
     }
+    printf("expansion host seconds: pop %.3f generate %.3f commit %.3f auto_save %.3f; gpu calls %ld\n", tPop, tGen, tCommit, tSave, gpuCalls);
     setNeighborRadius();
     return true;
 }

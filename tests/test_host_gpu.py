@@ -53,3 +53,22 @@ def test_reconstruct_plane(tmp_path):
     # warm start from the MVS file (TMVS.cpp:87-89): loads cameras + patches and re-refines them as seeds
     out3 = run_tmvs(d, os.path.join(d, "seed.mvs"), ["--no-expand", "--out-dir", d2])
     assert "seeds kept" in out3
+
+
+def test_reconstruct_two_gpus_identical(tmp_path):
+    """--gpus 2 shards every batch over two devices; the output is byte-identical to the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = abi.readme_config()
+    cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD, cfg.cellSize = 7, 15, 7 / 3.0, 2, 8
+    sc = scene.SynthScene(cfg, nviews=5, width=320, height=240, seed=1234, tex_size=1024)
+    d = str(tmp_path)
+    path = mvsio.write_nvm_scene(d, sc, n_seeds=16)
+    mvsio.write_config(os.path.join(d, "config.txt"), cfg)
+    d1, d2 = os.path.join(d, "g1"), os.path.join(d, "g2")
+    os.makedirs(d1)
+    os.makedirs(d2)
+    run_tmvs(d, path, ["--out-dir", d1, "--gpus", "1"])
+    run_tmvs(d, path, ["--out-dir", d2, "--gpus", "2"])
+    assert open(os.path.join(d1, "exp.mvs"), "rb").read() == open(os.path.join(d2, "exp.mvs"), "rb").read()
