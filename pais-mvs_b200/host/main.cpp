@@ -6,7 +6,7 @@
  *
  * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
  * round, default 1024), --device D, --gpus N (shard every batch over N GPUs), --seed S (run seed of the counter-based PSO
- * RNG), --no-expand, -V (verbose),
+ * RNG), --autosave-seconds T (spacing of auto_save.mvs checkpoints, default 5), --no-expand, -V (verbose),
  * --convert IN OUT.mvs (load + write only: needs no GPU).
  */
 #include <chrono>
@@ -33,6 +33,7 @@ int main(int argc, char **argv) {
     std::string mode, input, configFile = "config.txt", outDir, imageDir, convertOut;
     int roundSize = 1024, device = 0, gpus = 1;
     unsigned long long seed = 42;
+    double autosave = 5.0;
     bool expand = true, verbose = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -45,6 +46,7 @@ int main(int argc, char **argv) {
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
         else if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
         else if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
+        else if (a == "--autosave-seconds" && i + 1 < argc) autosave = atof(argv[++i]);
         else if (a == "--no-expand") expand = false;
         else if (a == "-V") verbose = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -68,6 +70,7 @@ int main(int argc, char **argv) {
     mvs.device = device;
     mvs.numGpus = gpus > 0 ? gpus : 1;
     mvs.rngSeed = seed;
+    mvs.autosaveSeconds = autosave;
     mvs.verbose = verbose;
     mvs.imageDir = imageDir;
 

@@ -86,6 +86,7 @@ public:
     int device = 0;                    /* first device */
     int numGpus = 1;                   /* devices device .. device+numGpus-1, candidates sharded by index */
     uint64_t rngSeed = 42;
+    double autosaveSeconds = 5.0;      /* minimum spacing of auto_save.mvs checkpoints */
     bool verbose = false;
     std::string imageDir;              /* prefix for camera image files */
     long refinedCount = 0;             /* patches sent through refine() */

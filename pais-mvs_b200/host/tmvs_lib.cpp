@@ -647,6 +647,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     struct Cand { int parent, cam, cx, cy; };
     typedef std::chrono::steady_clock Clock;
     double tPop = 0, tGen = 0, tCommit = 0, tSave = 0;
+    Clock::time_point lastSave = Clock::now();
     long gpuCalls = 0;
     for (int round = 0;; ++round) {
         /* 1. pop up to roundSize parents in strategy order */
@@ -730,8 +731,11 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
         if (verbose)
             printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), nCands, accepted,
                    patches.size(), byPriorityQueueSize());
-        if (patches.size() / 500 > saveTime) {   /* mvs.cpp:265-268 */
+        /* mvs.cpp:265-268 checkpoints every 500 accepted patches; at GPU speed that is every few milliseconds and the
+         * rewrite of the whole file becomes quadratic, so checkpoints are additionally spaced autosaveSeconds apart */
+        if (patches.size() / 500 > saveTime && std::chrono::duration<double>(Clock::now() - lastSave).count() >= autosaveSeconds) {
             Clock::time_point ts0 = Clock::now();
+            lastSave = ts0;
             saveTime = patches.size() / 500;
             writeMVS("auto_save.mvs");
             tSave += std::chrono::duration<double>(Clock::now() - ts0).count();
