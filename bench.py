@@ -292,7 +292,7 @@ def run_gpu(args):
                              "note": "algorithmic tap-bytes model of SURVEY.md 8(d); the kernel is FP64-pipe bound, see DESIGN.md"}}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ncpu = args.cpu_patches if args.cpu_patches > 0 else max(cores * 128, 64)
+            ncpu = args.cpu_patches if args.cpu_patches > 0 else max(cores * 512, 256)     # ~10-20 s of CPU work
             dt, ckept, how = cpu_reference_run(cfg, sc, ncpu, cores)
             line["cpu_baseline"] = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d candidate patches of the same workload, OpenMP over patches on %d host threads, %.1f s; %s"

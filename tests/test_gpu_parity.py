@@ -205,7 +205,7 @@ def test_refine_golden():
     print("refine golden: worst relative deviation %.3g" % worst)
 
 
-@pytest.mark.parametrize("case", ["expand_r7", "seed_r7", "wide_arc", "occluded", "gradient_lod", "p5_defaults", "v12"])
+@pytest.mark.parametrize("case", ["expand_r7", "seed_r7", "wide_arc", "occluded", "gradient_lod", "p5_defaults", "v12", "v16_p32", "r17_wide"])
 def test_refine_vs_oracle(case):
     cfg = abi.readme_config()
     cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = 7, 15, 7 / 3.0, 2
@@ -229,6 +229,13 @@ def test_refine_vs_oracle(case):
     elif case == "v12":
         kw.update(nviews=12, arc_deg=35.0)
         n = 16
+    elif case == "v16_p32":             # BASELINE.json config 3 shape: 16 views, 32 particles x 50 iterations
+        kw.update(nviews=16, arc_deg=35.0)
+        cfg.particleNum, cfg.maxIteration = 32, 50
+        n = 8
+    elif case == "r17_wide":            # window wider than a warp: two column passes
+        cfg.patchRadius, cfg.patchSize, cfg.distWeighting = 17, 35, 17 / 3.0
+        n = 12
     sc = scene.SynthScene(cfg, **kw)
     if case == "occluded":              # one view shows unrelated texture: correlation test removes it (patch.cpp:703)
         other = scene.SynthScene(cfg, nviews=1, width=400, height=300, seed=999, with_edge=True, tex_size=512)
