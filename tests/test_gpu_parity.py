@@ -144,15 +144,16 @@ def test_fitness_golden(small_scene):
 @pytest.mark.parametrize("nviews,radius,weights", [(5, 7, (0, 0, 0)), (5, 15, (1, 1, 0)), (3, 4, (1, 1, 1)), (12, 7, (1, 1, 1)),
                                                    (20, 5, (1, 1, 0)), (40, 3, (1, 0, 1)), (1, 6, (1, 1, 0)), (2, 6, (1, 1, 1)),
                                                    (6, 5, (1, 1, 0)), (7, 9, (0, 1, 1)), (8, 17, (1, 1, 0)), (9, 9, (1, 0, 0)),
-                                                   (16, 21, (1, 1, 1)), (4, 21, (1, 1, 0))])
+                                                   (16, 21, (1, 1, 1)), (4, 21, (1, 1, 0)), (64, 3, (1, 1, 0)), (5, 31, (1, 1, 0))])
 def test_fitness_vs_oracle(nviews, radius, weights):
     """Every lane-per-column instantiation family (V = 1..16, narrow windows with row groups, windows wider than a warp),
     the generic V > 16 two-pass path and the checked path; borders (DBL_MAX), masked pixels, all LODs."""
     cfg = abi.readme_config()
     cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = radius, 2 * radius + 1, radius / 3.0, 2
     cfg.adaptiveDistanceEnable, cfg.adaptiveDifferenceEnable, cfg.adaptiveGradientEnable = weights
-    sc = scene.SynthScene(cfg, nviews=nviews, width=400, height=300, seed=7 + nviews, with_edge=True, tex_size=1024,
-                          background=10, arc_deg=30.0)
+    big = radius > 21                   # PMVS_MAX_RADIUS = 31: a 63 x 63 window needs a larger image
+    sc = scene.SynthScene(cfg, nviews=nviews, width=560 if big else 400, height=420 if big else 300, seed=7 + nviews, with_edge=True,
+                          tex_size=1024, background=10, arc_deg=30.0)
     o = orc.Oracle(cfg, sc.records)
     patches = sc.patches(60, seed=3, extent=2.4)
     worst, n_max, n = 0.0, 0, 0
@@ -173,6 +174,11 @@ def test_fitness_empty_and_ragged(small_scene):
     cfg, sc = small_scene
     with PatchRefiner(cfg, sc.records) as pr:
         assert pr.fitness((abi.PmvsHypothesis * 0)()) == []
+        assert len(pr.refine((abi.PmvsPatchIn * 0)())) == 1          # n = 0: nothing launched, nothing written
+        few = sc.patches(2, seed=1)
+        few[0].nCam = 2                      # fewer cameras than minCamNum: dropped in-band (patch.cpp:118-123)
+        out = pr.refine(few)
+        assert out[0].drop == 1 and out[0].fitness == abi.DBL_MAX and out[0].priority == abi.DBL_MAX and out[1].drop == 0
         hy = scene.hypotheses_from_patches(sc, sc.patches(3, seed=1), cfg, per_patch=1)
         hy[0].nCam = 1                       # single view: mean == c, avgSad == 0
         hy[1].nCam = 0                       # no view at all: invalid context
