@@ -146,6 +146,7 @@ __device__ inline void patch_from_in(const PmvsPatchIn &in, PatchS &p) {   /* Ab
     p.status = 0;
     p.windowEvals = 0;
     p.flag = 0;
+    p.visValid = 0;
 }
 __device__ inline void patch_to_out(const PatchS &p, PmvsPatchOut &o) {
     for (int k = 0; k < 3; ++k) {

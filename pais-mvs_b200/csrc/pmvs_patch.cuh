@@ -22,6 +22,10 @@ struct PatchS {
     unsigned evals, status, windowEvals;
     int flag, nx, ny;
     uint16_t camIdx[PMVS_MAX_VIEWS];
+    /* memo of the last removeInvisibleCamera() that removed nothing: its inputs (see cta_remove_invisible) */
+    double visCenter[3], visNormal[3];
+    int visValid, visRef, visLOD, visN;
+    uint16_t visCam[PMVS_MAX_VIEWS];
 };
 
 /* everything one CTA owns in shared memory */
@@ -421,6 +425,18 @@ __device__ __noinline__ void cta_remove_invisible(const DevScene &S, CtaS &c, do
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     if (p.drop) return;                                   /* uniform: p.drop was written before the last barrier */
     const int V = p.nCam, r = S.cfg.patchRadius, ps = S.cfg.patchSize, SS = ps * ps;
+    /* removeInvisibleCamera is a pure function of (center, normal, reference camera, LOD, camera list). The caller's
+     * trailing call (mvs.cpp:215, :574) very often repeats the call made inside refine() (:162) with identical inputs —
+     * nothing was removed and the reference camera / LOD were re-selected to the same values — and then it would
+     * reproduce the same correlation and remove nothing again: skip it. */
+    if (tid == 0) {
+        bool same = p.visValid && p.visRef == p.refCamIdx && p.visLOD == p.LOD && p.visN == V;
+        for (int k = 0; same && k < 3; ++k) same = p.visCenter[k] == p.center[k] && p.visNormal[k] == p.normal[k];
+        for (int k = 0; same && k < V; ++k) same = p.visCam[k] == p.camIdx[k];
+        p.flag = same ? 2 : 0;
+    }
+    __syncthreads();
+    if (p.flag == 2) return;
     cta_build_ctx(S, c);
     const EvalCtx &E = c.E;
     if (!E.valid) {                                       /* missing pyramid level: cannot be evaluated */
@@ -528,6 +544,14 @@ __device__ __noinline__ void cta_remove_invisible(const DevScene &S, CtaS &c, do
                 }
         p.nCam = n;
         if (p.nCam < S.cfg.minCamNum) p.drop = 1;
+        p.visValid = (nRemove == 0 && !p.drop) ? 1 : 0;
+        if (p.visValid) {
+            p.visRef = p.refCamIdx;
+            p.visLOD = p.LOD;
+            p.visN = V;
+            for (int k = 0; k < 3; ++k) { p.visCenter[k] = p.center[k]; p.visNormal[k] = p.normal[k]; }
+            for (int k = 0; k < V; ++k) p.visCam[k] = p.camIdx[k];
+        }
     }
     __syncthreads();
 }
