@@ -157,7 +157,11 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
+    from pmvs_b200 import lib as pmvs_lib
     from pmvs_b200.api import PatchRefiner
+
+    if not os.path.exists(pmvs_lib.LIB_PATH) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        pmvs_lib.build()            # fresh checkout: compile the CUDA library (there is still no CPU path)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -8,7 +8,7 @@ import subprocess
 from . import abi
 
 PKG_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libpmvs_b200.so")
+LIB_PATH = os.environ.get("PMVS_LIB") or os.path.join(PKG_ROOT, "lib", "libpmvs_b200.so")      # PMVS_LIB: build variants (tuning)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 
 # every symbol include/pmvs_b200.h declares
