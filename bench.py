@@ -162,6 +162,10 @@ def run_gpu(args):
 
     if not os.path.exists(pmvs_lib.LIB_PATH) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
         pmvs_lib.build()            # fresh checkout: compile the CUDA library (there is still no CPU path)
+    for _ in range(600):            # other ranks wait for rank 0's build
+        if os.path.exists(pmvs_lib.LIB_PATH):
+            break
+        time.sleep(0.5)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
