@@ -53,9 +53,9 @@ static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t he
     off += sizeof(ViewS) * (size_t)vcap;
     off = (off + 15) & ~(size_t)15;
     pl.distOff = off;
-    off += sizeof(double) * (size_t)ps * ps;
+    off += sizeof(double) * ((size_t)PMVS_DIST_PAD(ps) + 64);     /* distance weights + exp table */
     pl.warpOff = off;
-    pl.perWarp = (((size_t)vcap * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_COLV_DOUBLES(vcap);
+    pl.perWarp = (((size_t)vcap * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_COLV_DOUBLES(vcap, ps);
     off += sizeof(double) * pl.perWarp * nWarps;
     pl.corrOff = off;
     if (withCorr) off += sizeof(double) * (size_t)vcap * vcap;
@@ -84,7 +84,10 @@ __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArg
     W.H = base;
     W.xs = base + (size_t)a.vcap * 9;
     W.ys = W.xs + a.ps;
-    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES(a.vcap);
+    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES(a.vcap, a.ps);
+    W.gv = W.colv + PMVS_COLV_SLOTS(a.vcap);
+    W.rowf = W.gv + PMVS_GV_DOUBLES * 16;
+    W.rowi = (int2 *)(W.rowf + PMVS_PS_PAD(a.ps));
     return W;
 }
 
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(128) fitness_batch_kernel(const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     double *sDistW = (double *)(smem + a.distOff);
     for (int k = tid; k < a.ps * a.ps; k += blockDim.x) sDistW[k] = S.distW[k];
+    load_exp_table(sDistW, a.ps, tid, blockDim.x);
     /* one EvalCtx + view table per warp: ctaOff holds NW contexts, viewOff NW*vcap views */
     EvalCtx &E = ((FitWarpS *)(smem + a.ctaOff))[warp].E;
     if (lane == 0) E.view = (ViewS *)(smem + a.viewOff) + (size_t)warp * a.vcap;
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
     double *sDistW = (double *)(smem + a.distOff);
     double *corr = (double *)(smem + a.corrOff);
     for (int k = tid; k < a.ps * a.ps; k += blockDim.x) sDistW[k] = S.distW[k];
+    load_exp_table(sDistW, a.ps, tid, blockDim.x);
     if (tid == 0) {
         c.E.view = (ViewS *)(smem + a.viewOff);
         c.part = (ParticleS *)(smem + a.ctaOff + ((sizeof(CtaS) + 15) & ~(size_t)15));
@@ -664,7 +669,7 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
     }
     if (const char *envNw = getenv("PMVS_NW")) {       /* tuning override, 4..8 */
         const int w = atoi(envNw);
-        if (w >= 4 && w <= 16) NW = w;
+        if (w >= 4 && w <= 8) NW = w;
     }
     int nPart = ctx->cfg.particleNum * 2;
     if (nPart > PMVS_MAX_PARTICLES) nPart = PMVS_MAX_PARTICLES;
@@ -674,7 +679,7 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
     typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *);
     const char *envRegs = getenv("PMVS_REGS");
     const bool lean = NW <= 5 && (envRegs ? atoi(envRegs) == 96 : PMVS_DEFAULT_LEAN);
-    RefineFn fn = lean ? (RefineFn)refine_kernel<160, 4> : (NW > 8 ? (RefineFn)refine_kernel<512, 1> : (RefineFn)refine_kernel<256, 2>);
+    RefineFn fn = lean ? (RefineFn)refine_kernel<160, 4> : (RefineFn)refine_kernel<256, 2>;
     const int warpsPerSm = lean ? 20 : 16;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     int perSm = 0;

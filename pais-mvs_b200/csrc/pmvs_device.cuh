@@ -29,7 +29,11 @@
 #define PMVS_MAX_PS (2 * PMVS_MAX_RADIUS + 1)
 #define PMVS_FULL 0xffffffffu
 #define PMVS_COLV_VIEWS(vcap) ((vcap) < 5 ? 5 : ((vcap) > 16 ? 16 : (vcap)))
-#define PMVS_COLV_DOUBLES(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
+#define PMVS_COLV_SLOTS(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
+#define PMVS_GV_DOUBLES 6                    /* per non-reference view: h1, h4, h7, quad pointer, cols, spare */
+#define PMVS_PS_PAD(ps) (((ps) + 1) & ~1)
+/* per-warp area of the column loop: per-lane slots | compact non-reference view table | per-row {fy} | per-row {py*cols, sel} */
+#define PMVS_COLV_DOUBLES(vcap, ps) (PMVS_COLV_SLOTS(vcap) + PMVS_GV_DOUBLES * 16 + 2 * PMVS_PS_PAD(ps))
 
 struct DevLevel {
     const uint32_t *quad;
@@ -64,13 +68,17 @@ struct EvalCtx {
     const double *refEdge;
     ViewS *view;
     int refCols, refRows, refCam, LOD, V, valid;
+    int refView, _pad;   /* index of the reference camera in view[] (-1: not among the views) */
 };
 /* per-warp scratch (shared memory) */
 struct WarpWork {
     double *H;      /* V*9 */
     double *xs;     /* patchSize */
     double *ys;     /* patchSize */
-    double *colv;   /* PMVS_COLV_DOUBLES(vcap): per-lane column constants of the unchecked loop */
+    double *colv;   /* PMVS_COLV_SLOTS(vcap): per-lane column constants of the unchecked loop */
+    double *gv;     /* PMVS_GV_DOUBLES * 16: compact table of the non-reference views */
+    double *rowf;   /* PMVS_PS_PAD(ps): fractional part of each window row in the reference view */
+    int2 *rowi;     /* PMVS_PS_PAD(ps): {floor(y) * refCols, 2 * (cvRound(y) - floor(y))} per window row */
 };
 
 __device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -388,15 +396,27 @@ __device__ __forceinline__ double quad_bilinear_fast(const uint32_t *__restrict_
 }
 
 /*
- * Unchecked sample loop for exactly V views (compile-time, 1..16): lane = one window column (several row groups when
- * the window is narrow, several column passes when it is wider than 32), so the x-dependent part of every homography
- * row, A = H0*x+H2, B = H3*x+H5, C = H6*x+H8, is computed once per evaluation and parked in a per-lane shared-memory
- * slot (registers are the scarce resource: the slots buy ptxas room to interleave the per-view chains); a sample then
- * costs three fma for the projective coordinates. Views are processed in chunks of <= 5, stage by stage across the
- * chunk (all w, all reciprocal seeds, each refinement step, ...) so neighbouring instructions are independent; the
- * body is branch-free. The reference view (H = I, patch.cpp:317-319) goes through the same arithmetic: A = x, the
- * y-part of w is 0 and w = 1 exactly, so its sample is (x, y) bit for bit. Each lane sums its rows in ascending
- * order, then the fixed xor-tree.
+ * Unchecked sample loop for exactly V views (compile-time, 2..16), one of which is the reference view.
+ *
+ * Lane = one window column (several row groups when the window is narrow, several column passes when it is wider
+ * than 32), so the x-dependent part of every homography row, A = H0*x+H2, B = H3*x+H5, C = H6*x+H8, is computed once
+ * per evaluation and parked in a per-lane shared-memory slot (registers are the scarce resource); a sample of a
+ * non-reference view then costs, on the FP64 pipe:
+ *   3 fma   projective coordinates  X = h1*y+A, Y = h4*y+B, w = h7*y+C
+ *   3 fma   reciprocal: MUFU.RCP64H seed r0, r = r0*(1+e+e^2), e = 1-w*r0
+ *   2 mul   ix = X*r, iy = Y*r
+ *   2 add   round-down magic adds: low words = px, py (the tap address)
+ *   2 add   fy = iy - floor(iy)
+ *   3 fma   bilinear blend (patch.cpp:1005-1017) without forming fx: with integer tap differences dx, dy, dxy,
+ *             c = g00 + fx*dx + fy*(dy + fx*dxy),  fx = ix - px
+ *               = fma(fy, fma(ix, dxy, dy - px*dxy), fma(ix, dx, g00 - px*dx))
+ *           the integer parts dy - px*dxy and g00 - px*dx are exact (IMAD, |.| < 2^22) and each fma rounds once, so
+ *           this is as accurate as the fx form and saves the two adds that would form fx.
+ *   3 add   cross-view mean and absolute deviation
+ * The reference view has H = I (patch.cpp:317-319): its sample is (x, y) bit for bit, so its pixel index and
+ * fractions are per-column / per-row constants (no homography, reciprocal or floor), and the background-mask pixel
+ * img(cvRound(y), cvRound(x)) (patch.cpp:986) is one of the four bytes of the tap word it loads anyway.
+ * The body is branch-free; each lane sums its rows in ascending order, then the fixed xor-tree.
  */
 __device__ __forceinline__ double lds_f64_v(unsigned a) {   /* ordered against the volatile stores below */
     double v;
@@ -404,23 +424,85 @@ __device__ __forceinline__ double lds_f64_v(unsigned a) {   /* ordered against t
     return v;
 }
 __device__ __forceinline__ void sts_f64_v(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ int2 lds_s32x2(unsigned a) {
+    int2 v;
+    asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+/* small signed integer -> f64. PMVS_CVT_MIX picks the pipe: the conversion unit (I2F.F64, 16 lanes/SM) or one FP64 add
+ * on the biased-exponent form (2^52 + 2^31 + n) - (2^52 + 2^31); both exact. */
+#ifndef PMVS_CVT_MIX
+#define PMVS_CVT_MIX 0
+#endif
+#ifndef PMVS_ROWS
+#define PMVS_ROWS 2             /* window rows per loop trip */
+#endif
+#ifndef PMVS_TWO_ROW_VIEWS
+#define PMVS_TWO_ROW_VIEWS 4    /* up to this many non-reference views, both rows of a trip are staged together */
+#endif
+#ifndef PMVS_CHUNK
+#define PMVS_CHUNK 4            /* non-reference views staged together in the chunked row */
+#endif
+__device__ __forceinline__ double cvt_a(int n) { return PMVS_CVT_MIX >= 2 ? s2d(n) : (double)n; }
+__device__ __forceinline__ double cvt_b(int n) { return PMVS_CVT_MIX >= 1 ? s2d(n) : (double)n; }
+
+/* exp(x) for the difference weight exp(-avgSad^2/diffWeighting) (patch.cpp:1034) when -700 <= x <= 0 is guaranteed:
+ * x = (k/64) ln2 + r, |r| <= ln2/128; exp = 2^(k>>6) * T[k&63] * (1 + r + ... + r^5/120) (remainder < 4e-17),
+ * T[i] = 2^(i/64) from shared memory. */
+__constant__ double kExpTab64[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+#define PMVS_DIST_PAD(ps) (((ps) * (ps) + 1) & ~1)   /* the table sits behind the distance weights in shared memory */
+__device__ __forceinline__ void load_exp_table(double *sDistW, int ps, int tid, int nthreads) {
+    for (int k = tid; k < 64; k += nthreads) sDistW[PMVS_DIST_PAD(ps) + k] = kExpTab64[k];
+}
+__device__ __forceinline__ double exp_table(double x, unsigned tabA) {
+    const double t = fma(x, 92.33248261689366, 6755399441055744.0);     /* 64/ln2; low word = round-to-nearest k */
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -0.01083042469326756, x);                              /* ln2/64 split: hi has 32 significant bits */
+    r = fma(kd, -2.9815858269852933e-12, r);
+    const double T = lds_f64(tabA + 8u * (unsigned)(k & 63));
+    double q = fma(r, 8.33333333333333321769e-03, 4.16666666666666643537e-02);
+    q = fma(r, q, 1.66666666666666657415e-01);
+    q = fma(r, q, 0.5);
+    q = fma(r, q, 1.0);
+    const double p = fma(T * r, q, T);
+    return __hiloint2double(__double2hiint(p) + ((k >> 6) << 20), __double2loint(p));
+}
 
 template <int N>
 struct ColumnTaps {
-    double fx[N], fy[N];
+    double ix[N], fy[N];
     uint32_t q[N];
+    int px[N];
 };
 
-/* projective coordinates, floors and tap loads of views [v0, v0+N) for the row y of this lane's column;
- * cvA = this lane's slot base: A,B,C of view v at cvA + 256*(3v + {0,1,2}) */
+/* projective coordinates, floors and tap loads of the non-reference views [k0, k0+N) for the row y of this lane's
+ * column; gvA = compact view table (h1, h4, h7, quad, cols per view), cvA = this lane's slot base: A,B,C of view k at
+ * cvA + 256*(3k + {0,1,2}) */
 template <int N>
-__device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, unsigned cvA, int v0, double y, ColumnTaps<N> &t) {
+__device__ __forceinline__ void column_coords(unsigned gvA, unsigned cvA, int k0, double y, ColumnTaps<N> &t) {
     double w[N], r[N], e[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) w[k] = fma(lds_f64(hA + 72u * (v0 + k) + 56u), y, lds_f64_v(cvA + 256u * (3 * (v0 + k) + 2)));
+    for (int k = 0; k < N; ++k) w[k] = fma(lds_f64(gvA + 48u * (k0 + k) + 16u), y, lds_f64_v(cvA + 256u * (3 * (k0 + k) + 2)));
 #pragma unroll
     for (int k = 0; k < N; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[k]) : "d"(w[k]));
-    /* r = r0*(1 + e + e^2), e = 1 - w*r0: residual e^3 ~ 2^-60 from the ~2^-20 seed, three dependent fma */
 #pragma unroll
     for (int k = 0; k < N; ++k) e[k] = fma(-w[k], r[k], 1.0);
 #pragma unroll
@@ -429,80 +511,123 @@ __device__ __forceinline__ void column_coords(unsigned viewA, unsigned hA, unsig
     for (int k = 0; k < N; ++k) r[k] = fma(r[k], e[k], r[k]);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        t.fx[k] = fma(lds_f64(hA + 72u * (v0 + k) + 8u), y, lds_f64_v(cvA + 256u * (3 * (v0 + k)))) * r[k];          /* ix */
-        t.fy[k] = fma(lds_f64(hA + 72u * (v0 + k) + 32u), y, lds_f64_v(cvA + 256u * (3 * (v0 + k) + 1))) * r[k];     /* iy */
+        t.ix[k] = fma(lds_f64(gvA + 48u * (k0 + k)), y, lds_f64_v(cvA + 256u * (3 * (k0 + k)))) * r[k];
+        t.fy[k] = fma(lds_f64(gvA + 48u * (k0 + k) + 8u), y, lds_f64_v(cvA + 256u * (3 * (k0 + k) + 1))) * r[k];     /* iy */
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        w[k] = __dadd_rd(t.fx[k], PMVS_MAGIC_FLOOR);
+        w[k] = __dadd_rd(t.ix[k], PMVS_MAGIC_FLOOR);
         r[k] = __dadd_rd(t.fy[k], PMVS_MAGIC_FLOOR);
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const unsigned va = viewA + (unsigned)(v0 + k) * (unsigned)sizeof(ViewS);
-        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(va + (unsigned)offsetof(ViewS, quad));
-        const int cols = lds_s32(va + (unsigned)offsetof(ViewS, cols));
-        t.q[k] = __ldg(quad + (__double2loint(r[k]) * cols + __double2loint(w[k])));
+        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(gvA + 48u * (k0 + k) + 24u);
+        const int cols = lds_s32(gvA + 48u * (k0 + k) + 32u);
+        t.px[k] = __double2loint(w[k]);
+        t.q[k] = __ldg(quad + (__double2loint(r[k]) * cols + t.px[k]));
     }
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        t.fx[k] = t.fx[k] - (w[k] - PMVS_MAGIC_FLOOR);
-        t.fy[k] = t.fy[k] - (r[k] - PMVS_MAGIC_FLOOR);
-    }
+    for (int k = 0; k < N; ++k) t.fy[k] = t.fy[k] - (r[k] - PMVS_MAGIC_FLOOR);
 }
 
-/* bilinear blend in difference form (see quad_bilinear_fast): byte extraction by PRMT, tap differences in integers,
- * int->f64 on the (otherwise idle) conversion pipe */
 template <int N>
 __device__ __forceinline__ void column_blend(const ColumnTaps<N> &t, double *c) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const int g00 = (int)__byte_perm(t.q[k], 0, 0x4440), g01 = (int)__byte_perm(t.q[k], 0, 0x4441);
         const int g10 = (int)__byte_perm(t.q[k], 0, 0x4442), g11 = (int)__byte_perm(t.q[k], 0, 0x4443);
-        const int idx = g01 - g00, idy = g10 - g00;
-        const double c00 = (double)g00, dx = (double)idx, dy = (double)idy, dxy = (double)(g11 - g10 - idx);
-        c[k] = fma(t.fy[k], fma(t.fx[k], dxy, dy), fma(t.fx[k], dx, c00));
+        /* negated differences, so the integer parts are plain multiply-adds and the sign rides on the fma operand */
+        const int ndx = g00 - g01, idy = g10 - g00, ndxy = g10 - g11 - ndx;
+        const int k0 = t.px[k] * ndx + g00, k1 = t.px[k] * ndxy + idy;
+        c[k] = fma(t.fy[k], fma(-t.ix[k], cvt_a(ndxy), cvt_b(k1)), fma(-t.ix[k], cvt_a(ndx), cvt_b(k0)));
     }
 }
 
-/* cross-view mean and average absolute deviation (patch.cpp:1019-1027) */
-template <int V>
-__device__ __forceinline__ double avg_sad(const double *c, double invV) {
-    double mean = 0;
-#pragma unroll
-    for (int v = 0; v < V; ++v) mean += c[v];
-    mean *= invV;
-    double sad = 0;
-#pragma unroll
-    for (int v = 0; v < V; ++v) sad += fabs(c[v] - mean);
-    return sad * invV;
+/* the reference view's sample of one row: tap word, mask bit, colour */
+struct RefColumn {
+    const uint32_t *__restrict__ quad;   /* refQuad + floor(x) */
+    double fx;
+    int selx;                            /* cvRound(x) - floor(x) */
+};
+__device__ __forceinline__ double ref_sample(const RefColumn &rc, int2 ri, double fy, bool &keep) {
+    const uint32_t q = __ldg(rc.quad + ri.x);
+    keep = __byte_perm(q, 0, 0x4440 + ri.y + rc.selx) != 0;                            /* patch.cpp:986 */
+    const int g00 = (int)__byte_perm(q, 0, 0x4440), g01 = (int)__byte_perm(q, 0, 0x4441);
+    const int g10 = (int)__byte_perm(q, 0, 0x4442), g11 = (int)__byte_perm(q, 0, 0x4443);
+    const int idx = g01 - g00, idy = g10 - g00, idxy = g11 - g10 - idx;
+    return fma(fy, fma(rc.fx, cvt_a(idxy), cvt_b(idy)), fma(rc.fx, cvt_a(idx), cvt_b(g00)));
 }
 
-template <int V, int V0>
-__device__ __forceinline__ void row_chunks(unsigned viewA, unsigned hA, unsigned cvA, double y, double *c) {
-    if constexpr (V0 < V) {
-        constexpr int N = (V - V0) < 4 ? (V - V0) : 4;
+/* cross-view mean and summed absolute deviation (patch.cpp:1019-1027; the division by V is folded into the callers'
+ * constants) */
+template <int N>
+__device__ __forceinline__ double tree_sum(const double *c) {       /* pairwise: depth log2(N) instead of N */
+    if constexpr (N == 1) return c[0];
+    else return tree_sum<N / 2>(c) + tree_sum<N - N / 2>(c + N / 2);
+}
+template <int V>
+__device__ __forceinline__ double sum_abs_dev(const double *c, double invV) {
+    const double mean = tree_sum<V>(c) * invV;
+    double d[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) d[v] = fabs(c[v] - mean);
+    return tree_sum<V>(d);
+}
+
+template <int NG, int K0>
+__device__ __forceinline__ void row_chunks(unsigned gvA, unsigned cvA, double y, double *c) {
+    if constexpr (K0 < NG) {
+        constexpr int N = (NG - K0) < PMVS_CHUNK ? (NG - K0) : PMVS_CHUNK;
         ColumnTaps<N> t;
-        column_coords<N>(viewA, hA, cvA, V0, y, t);
-        column_blend<N>(t, c + V0);
-        row_chunks<V, V0 + N>(viewA, hA, cvA, y, c);
+        column_coords<N>(gvA, cvA, K0, y, t);
+        column_blend<N>(t, c + K0);
+        row_chunks<NG, K0 + N>(gvA, cvA, y, c);
     }
 }
 
-template <int V>
+/* FAST: no gradient weight and the difference weight's exponent provably in [-700, 0] — the distance weight is
+ * always read (the table holds ones when it is disabled) and the difference weight always evaluated (negK = 0 when it
+ * is disabled), so the row loop carries no configuration flags. */
+template <int V, bool FAST>
 __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
-                                             const double *__restrict__ Hw, const double *__restrict__ xs,
-                                             const double *__restrict__ ys, double *colv, int nx, int ny, double &fitOut, double &swOut) {
+                                             const double *__restrict__ sExpT, const WarpWork &W, int nx, int ny, double &fitOut,
+                                             double &swOut) {
+    constexpr int NG = V - 1;                       /* non-reference views */
     const int lane = threadIdx.x & 31;
     const int G = nx <= 16 ? 32 / nx : 1;          /* row groups sharing the warp (narrow windows) */
-    const unsigned hA = smem_addr(Hw), ysA = smem_addr(ys), xsA = smem_addr(xs), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
-    const unsigned cvA = smem_addr(colv) + 8u * lane;
+    const unsigned hA = smem_addr(W.H), ysA = smem_addr(W.ys), xsA = smem_addr(W.xs), distA = smem_addr(sDistW);
+    const unsigned gvA = smem_addr(W.gv), rfA = smem_addr(W.rowf), riA = smem_addr(W.rowi), tabA = smem_addr(sExpT);
+    const unsigned cvA = smem_addr(W.colv) + 8u * lane;
     const double invV = 1.0 / (double)V;
-    const bool useDist = S.cfg.adaptiveDistanceEnable, useDiff = S.cfg.adaptiveDifferenceEnable, useGrad = S.cfg.adaptiveGradientEnable;
-    const double invDiffW = 1.0 / S.cfg.diffWeighting, gradW = S.cfg.gradientWeighting;
-    const uint32_t *__restrict__ refQuad = E.refQuad;
+    const bool useDist = FAST || S.cfg.adaptiveDistanceEnable, useDiff = FAST || S.cfg.adaptiveDifferenceEnable;
+    const bool useGrad = !FAST && S.cfg.adaptiveGradientEnable;
+    const double gradW = S.cfg.gradientWeighting;
+    /* exp argument = negK * (sum of deviations)^2 */
+    const double negK = S.cfg.adaptiveDifferenceEnable ? -(invV * invV) / S.cfg.diffWeighting : 0.0;
+    const bool expSafe = FAST;
     const double *__restrict__ refEdge = E.refEdge;
-    const int refCols = E.refCols;
+    const int refCols = E.refCols, refV = E.refView;
+
+    /* per-evaluation tables: compact non-reference view list, per-row constants of the reference view */
+    if (lane < NG) {
+        const int v = lane + (lane >= refV ? 1 : 0);
+        const ViewS &vw = E.view[v];
+        double *g = W.gv + PMVS_GV_DOUBLES * lane;
+        g[0] = W.H[9 * v + 1];
+        g[1] = W.H[9 * v + 4];
+        g[2] = W.H[9 * v + 7];
+        *(const uint32_t **)(g + 3) = vw.quad;
+        *(int *)(g + 4) = vw.cols;
+    }
+    for (int j = lane; j < ny; j += 32) {
+        const double y = W.ys[j];
+        const double ty = __dadd_rd(y, PMVS_MAGIC_FLOOR);
+        const int py = __double2loint(ty);
+        W.rowf[j] = y - (ty - PMVS_MAGIC_FLOOR);
+        W.rowi[j] = make_int2(py * refCols, 2 * (__double2int_rn(y) - py));
+    }
+    __syncwarp();
+
     double fit = 0, sw = 0;
     for (int i0 = 0; i0 < nx; i0 += 32) {          /* column passes (windows wider than the warp) */
         const int span = nx - i0 < 32 ? nx - i0 : 32;
@@ -510,51 +635,90 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         const bool active = G > 1 ? g < G : lane < span;
         const double x = lds_f64(xsA + 8u * (active ? i : i0));
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const unsigned h = hA + 72u * v;
-            sts_f64_v(cvA + 256u * (3 * v), fma(lds_f64(h), x, lds_f64(h + 16u)));
-            sts_f64_v(cvA + 256u * (3 * v + 1), fma(lds_f64(h + 24u), x, lds_f64(h + 40u)));
-            sts_f64_v(cvA + 256u * (3 * v + 2), fma(lds_f64(h + 48u), x, lds_f64(h + 64u)));
+        for (int k = 0; k < NG; ++k) {
+            const unsigned h = hA + 72u * (unsigned)(k + (k >= refV ? 1 : 0));
+            sts_f64_v(cvA + 256u * (3 * k), fma(lds_f64(h), x, lds_f64(h + 16u)));
+            sts_f64_v(cvA + 256u * (3 * k + 1), fma(lds_f64(h + 24u), x, lds_f64(h + 40u)));
+            sts_f64_v(cvA + 256u * (3 * k + 2), fma(lds_f64(h + 48u), x, lds_f64(h + 64u)));
         }
-        const int rx = __double2int_rn(x);
+        RefColumn rc;
+        const double tx = __dadd_rd(x, PMVS_MAGIC_FLOOR);
+        const int pxr = __double2loint(tx), rx = __double2int_rn(x);
+        rc.quad = E.refQuad + pxr;
+        rc.fx = x - (tx - PMVS_MAGIC_FLOOR);
+        rc.selx = rx - pxr;
         const int jEnd = active ? ny : 0;
+#if PMVS_ROWS == 1
+        for (int j = g; j < jEnd; j += G) {
+            const double y0 = lds_f64(ysA + 8u * j);
+            const int2 ri0 = lds_s32x2(riA + 8u * j);
+            bool keep0;
+            double c[V];
+            c[NG] = ref_sample(rc, ri0, lds_f64(rfA + 8u * j), keep0);
+            row_chunks<NG, 0>(gvA, cvA, y0, c);
+            const double s0 = sum_abs_dev<V>(c, invV);
+            double w0 = 1.0;
+            if (useDist) w0 = lds_f64(distA + 8u * (i * ny + j));                             /* patch.cpp:1030-1032 */
+            if (useDiff) {                                                                    /* patch.cpp:1033-1035 */
+                const double x0 = s0 * s0 * negK;
+                w0 *= expSafe ? exp_table(x0, tabA) : exp_nonpos(x0);
+            }
+            if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
+                const int rofs0 = ri0.x + (ri0.y ? refCols : 0) + pxr + rc.selx;
+                w0 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs0) * gradW));
+            }
+            w0 = keep0 ? w0 : 0.0;
+            sw += w0;
+            fit = fma(w0, s0, fit);
+        }
+#else
         for (int j = g; j < jEnd; j += 2 * G) {
             const bool two = j + G < jEnd;
             const int j2 = two ? j + G : j;
             const double y0 = lds_f64(ysA + 8u * j), y1 = lds_f64(ysA + 8u * j2);
-            const int rofs0 = __double2int_rn(y0) * refCols + rx, rofs1 = __double2int_rn(y1) * refCols + rx;
-            const bool keep0 = (__ldg(refQuad + rofs0) & 0xffu) != 0;                       /* patch.cpp:986 */
-            const bool keep1 = two && (__ldg(refQuad + rofs1) & 0xffu) != 0;
+            const int2 ri0 = lds_s32x2(riA + 8u * j), ri1 = lds_s32x2(riA + 8u * j2);
+            bool keep0, keep1;
             double s0, s1;
-            if constexpr (V <= 5) {
+            if constexpr (NG <= PMVS_TWO_ROW_VIEWS) {
                 /* both rows' tap loads are in flight before the first one is consumed */
-                ColumnTaps<V> ta, tb;
+                ColumnTaps<NG> ta, tb;
                 double ca[V], cb[V];
-                column_coords<V>(viewA, hA, cvA, 0, y0, ta);
-                column_coords<V>(viewA, hA, cvA, 0, y1, tb);
-                column_blend<V>(ta, ca);
-                column_blend<V>(tb, cb);
-                s0 = avg_sad<V>(ca, invV);
-                s1 = avg_sad<V>(cb, invV);
+                column_coords<NG>(gvA, cvA, 0, y0, ta);
+                column_coords<NG>(gvA, cvA, 0, y1, tb);
+                ca[NG] = ref_sample(rc, ri0, lds_f64(rfA + 8u * j), keep0);
+                cb[NG] = ref_sample(rc, ri1, lds_f64(rfA + 8u * j2), keep1);
+                column_blend<NG>(ta, ca);
+                column_blend<NG>(tb, cb);
+                s0 = sum_abs_dev<V>(ca, invV);
+                s1 = sum_abs_dev<V>(cb, invV);
             } else {
                 /* many views: one row at a time (a real loop, so the two rows' colours are never live together) */
                 s0 = s1 = 0;
+                keep0 = keep1 = false;
 #pragma unroll 1
                 for (int rrow = 0; rrow < 2; ++rrow) {
                     double c[V];
-                    row_chunks<V, 0>(viewA, hA, cvA, rrow ? y1 : y0, c);
-                    const double sv = avg_sad<V>(c, invV);
-                    if (rrow) s1 = sv;
-                    else s0 = sv;
+                    bool kp;
+                    c[NG] = ref_sample(rc, rrow ? ri1 : ri0, lds_f64(rfA + 8u * (rrow ? j2 : j)), kp);
+                    row_chunks<NG, 0>(gvA, cvA, rrow ? y1 : y0, c);
+                    const double sv = sum_abs_dev<V>(c, invV);
+                    if (rrow) { s1 = sv; keep1 = kp; }
+                    else { s0 = sv; keep0 = kp; }
                 }
             }
+            keep1 = keep1 && two;
             double w0 = 1.0, w1 = 1.0;
             if (useDist) {                                                                    /* patch.cpp:1030-1032 */
                 w0 = lds_f64(distA + 8u * (i * ny + j));
                 w1 = lds_f64(distA + 8u * (i * ny + j2));
             }
-            if (useDiff) { w0 *= exp_nonpos(-s0 * s0 * invDiffW); w1 *= exp_nonpos(-s1 * s1 * invDiffW); }    /* patch.cpp:1033-1035 */
+            if (useDiff) {                                                                    /* patch.cpp:1033-1035 */
+                const double x0 = s0 * s0 * negK, x1 = s1 * s1 * negK;
+                if (expSafe) { w0 *= exp_table(x0, tabA); w1 *= exp_table(x1, tabA); }
+                else { w0 *= exp_nonpos(x0); w1 *= exp_nonpos(x1); }
+            }
             if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
+                const int rofs0 = ri0.x + (ri0.y ? refCols : 0) + pxr + rc.selx, rofs1 = ri1.x + (ri1.y ? refCols : 0) + pxr + rc.selx;
                 w0 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs0) * gradW));
                 w1 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs1) * gradW));
             }
@@ -565,20 +729,27 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
             sw += w1;
             fit = fma(w1, s1, fit);
         }
+#endif
     }
-    fitOut = warp_sum(fit);
+    fitOut = warp_sum(fit) * invV;
     swOut = warp_sum(sw);
 }
 
 template <int V>
 __device__ __forceinline__ bool fitness_columns_dispatch(int nV, const DevScene &S, const EvalCtx &E, const double *sDistW,
-                                                         const WarpWork &W, int nx, int ny, double &fit, double &sw) {
-    if constexpr (V >= 1) {
+                                                         const double *sExpT, const WarpWork &W, int nx, int ny, double &fit,
+                                                         double &sw) {
+    if constexpr (V >= 2) {
         if (nV == V) {
-            fitness_columns<V>(S, E, sDistW, W.H, W.xs, W.ys, W.colv, nx, ny, fit, sw);
+            /* |deviation| <= 255 per view bounds the exponent of the difference weight */
+            const double xmin = -(255.0 * 255.0) / S.cfg.diffWeighting;
+            if (!S.cfg.adaptiveGradientEnable && S.cfg.adaptiveDistanceEnable && (!S.cfg.adaptiveDifferenceEnable || xmin >= -700.0))
+                fitness_columns<V, true>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
+            else
+                fitness_columns<V, false>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
             return true;
         }
-        return fitness_columns_dispatch<V - 1>(nV, S, E, sDistW, W, nx, ny, fit, sw);
+        return fitness_columns_dispatch<V - 1>(nV, S, E, sDistW, sExpT, W, nx, ny, fit, sw);
     } else {
         return false;
     }
@@ -634,8 +805,8 @@ __device__ __noinline__ double warp_fitness(const DevScene &S, const EvalCtx &E,
     if (inside) {
         ok = true;
         /* lane-per-column loop: every V in 1..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
-        if (VCAP == 8 && nx > 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, W, nx, ny, fit, sw)) {}
-        else if (VCAP == 16 && nx > 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, W, nx, ny, fit, sw)) {}
+        if (VCAP == 8 && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
+        else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     __syncwarp();
@@ -708,9 +879,13 @@ __device__ __forceinline__ void build_eval_ctx(const DevScene &S, EvalCtx &E, co
 /* after build_eval_ctx + barrier: a view without the level (cameras of different sizes) invalidates the context —
  * the reference would index a missing pyramid level there. */
 __device__ __forceinline__ void finish_eval_ctx(EvalCtx &E, int tid) {
-    if (tid == 0 && E.valid)
-        for (int v = 0; v < E.V; ++v)
+    if (tid == 0) {
+        E.refView = -1;
+        for (int v = 0; v < E.V; ++v) {
             if (E.view[v].quad == nullptr) E.valid = 0;
+            if (E.view[v].isRef && E.refView < 0) E.refView = v;
+        }
+    }
 }
 
 /* =====================================================================================================

@@ -11,14 +11,15 @@ import sys
 import tempfile
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
-so = os.path.join(ROOT, "pais-mvs_b200", "lib", "libpmvs_b200.so")
+so = os.path.abspath(os.environ.get("PMVS_LIB", os.path.join(ROOT, "pais-mvs_b200", "lib", "libpmvs_b200.so")))
+kern = os.environ.get("PMVS_KERNEL", "ILi256ELi2")     # template arguments of the profiled refine_kernel instantiation
 rep = sys.argv[1]
 detail = sys.argv[2] if len(sys.argv) > 2 else None
 with tempfile.TemporaryDirectory() as d:
     subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=d, stdout=subprocess.DEVNULL)
     cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
     txt = subprocess.run(["nvdisasm", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(txt) if l.startswith(".text._Z13refine_kernel")][0]
+start = [i for i, l in enumerate(txt) if l.startswith(".text._Z13refine_kernel" + kern)][0]
 end = [i for i, l in enumerate(txt) if i > start and l.startswith(".text.")]
 end = end[0] if end else len(txt)
 func, seq = "refine_kernel (main)", []
@@ -54,7 +55,7 @@ for f, v in sorted(agg.items(), key=lambda t: -t[1][0]):
     print("| %s | %.1f%% | %.1f%% | %s |" % (f, 100 * v[0] / ts, 100 * v[1] / ti, st))
 if detail:
     ks = [k for k in range(len(data)) if k < len(seq) and detail in seq[k]]
-    top = sorted(ks, key=lambda k: -int(data[k][ix["# Samples"]] or 0))[:40]
+    top = sorted(ks, key=lambda k: -int(data[k][ix["# Samples"]] or 0))[:int(os.environ.get("TOPN", "40"))]
     print("\ntop stalled instructions in", detail)
     for k in sorted(top):
         r = data[k]
