@@ -21,6 +21,11 @@
 #include "pmvs_pyramid.cuh"
 
 #define PMVS_VERSION "pmvs_b200 0.1 (sm_100a)"
+/* the alternative register budget of refine_kernel: __launch_bounds__(PMVS_ALT_T, PMVS_ALT_B) (160 x 4 = 96 registers) */
+#ifndef PMVS_ALT_T
+#define PMVS_ALT_T 160
+#define PMVS_ALT_B 4
+#endif
 #ifndef PMVS_DEFAULT_LEAN
 #define PMVS_DEFAULT_LEAN false
 #endif
@@ -678,9 +683,9 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
     /* two register budgets of the same kernel: 128 registers (16 warps/SM) or 96 (20 warps/SM, NW <= 5 only) */
     typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *);
     const char *envRegs = getenv("PMVS_REGS");
-    const bool lean = NW <= 5 && (envRegs ? atoi(envRegs) == 96 : PMVS_DEFAULT_LEAN);
-    RefineFn fn = lean ? (RefineFn)refine_kernel<160, 4> : (RefineFn)refine_kernel<256, 2>;
-    const int warpsPerSm = lean ? 20 : 16;
+    const bool lean = NW <= PMVS_ALT_T / 32 && (envRegs ? atoi(envRegs) != 128 : PMVS_DEFAULT_LEAN);
+    RefineFn fn = lean ? (RefineFn)refine_kernel<PMVS_ALT_T, PMVS_ALT_B> : (RefineFn)refine_kernel<256, 2>;
+    const int warpsPerSm = lean ? PMVS_ALT_T * PMVS_ALT_B / 32 : 16;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     int perSm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, NW * 32, pl.total));

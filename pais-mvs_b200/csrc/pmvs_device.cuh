@@ -435,8 +435,8 @@ __device__ __forceinline__ int2 lds_s32x2(unsigned a) {
 #ifndef PMVS_CVT_MIX
 #define PMVS_CVT_MIX 0
 #endif
-#ifndef PMVS_ROWS
-#define PMVS_ROWS 2             /* window rows per loop trip */
+#ifndef PMVS_PIPE_VIEWS
+#define PMVS_PIPE_VIEWS 0       /* up to this many non-reference views: one-row software-pipelined loop (0 = off) */
 #endif
 #ifndef PMVS_TWO_ROW_VIEWS
 #define PMVS_TWO_ROW_VIEWS 4    /* up to this many non-reference views, both rows of a trip are staged together */
@@ -549,13 +549,16 @@ struct RefColumn {
     double fx;
     int selx;                            /* cvRound(x) - floor(x) */
 };
-__device__ __forceinline__ double ref_sample(const RefColumn &rc, int2 ri, double fy, bool &keep) {
-    const uint32_t q = __ldg(rc.quad + ri.x);
-    keep = __byte_perm(q, 0, 0x4440 + ri.y + rc.selx) != 0;                            /* patch.cpp:986 */
+__device__ __forceinline__ double ref_blend(const RefColumn &rc, uint32_t q, double fy) {
     const int g00 = (int)__byte_perm(q, 0, 0x4440), g01 = (int)__byte_perm(q, 0, 0x4441);
     const int g10 = (int)__byte_perm(q, 0, 0x4442), g11 = (int)__byte_perm(q, 0, 0x4443);
     const int idx = g01 - g00, idy = g10 - g00, idxy = g11 - g10 - idx;
     return fma(fy, fma(rc.fx, cvt_a(idxy), cvt_b(idy)), fma(rc.fx, cvt_a(idx), cvt_b(g00)));
+}
+__device__ __forceinline__ double ref_sample(const RefColumn &rc, int2 ri, double fy, bool &keep) {
+    const uint32_t q = __ldg(rc.quad + ri.x);
+    keep = __byte_perm(q, 0, 0x4440 + ri.y + rc.selx) != 0;                            /* patch.cpp:986 */
+    return ref_blend(rc, q, fy);
 }
 
 /* cross-view mean and summed absolute deviation (patch.cpp:1019-1027; the division by V is folded into the callers'
@@ -648,14 +651,25 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         rc.fx = x - (tx - PMVS_MAGIC_FLOOR);
         rc.selx = rx - pxr;
         const int jEnd = active ? ny : 0;
-#if PMVS_ROWS == 1
+        if constexpr (NG <= PMVS_PIPE_VIEWS) {
+        /* software pipeline, one row per trip: the coordinates and tap loads of row j+G are issued while row j is
+         * blended, so a tap word is consumed one trip after its load */
+        ColumnTaps<NG> T;
+        uint32_t qr = 0;
+        if (g < jEnd) {
+            column_coords<NG>(gvA, cvA, 0, lds_f64(ysA + 8u * g), T);
+            qr = __ldg(rc.quad + lds_s32(riA + 8u * g));
+        }
         for (int j = g; j < jEnd; j += G) {
-            const double y0 = lds_f64(ysA + 8u * j);
-            const int2 ri0 = lds_s32x2(riA + 8u * j);
-            bool keep0;
+            const int jn = j + G < jEnd ? j + G : j;
+            ColumnTaps<NG> Tn;
+            column_coords<NG>(gvA, cvA, 0, lds_f64(ysA + 8u * jn), Tn);
+            const uint32_t qrn = __ldg(rc.quad + lds_s32(riA + 8u * jn));
+            const int sel = lds_s32(riA + 8u * j + 4u);
             double c[V];
-            c[NG] = ref_sample(rc, ri0, lds_f64(rfA + 8u * j), keep0);
-            row_chunks<NG, 0>(gvA, cvA, y0, c);
+            const bool keep0 = __byte_perm(qr, 0, 0x4440 + sel + rc.selx) != 0;              /* patch.cpp:986 */
+            c[NG] = ref_blend(rc, qr, lds_f64(rfA + 8u * j));
+            column_blend<NG>(T, c);
             const double s0 = sum_abs_dev<V>(c, invV);
             double w0 = 1.0;
             if (useDist) w0 = lds_f64(distA + 8u * (i * ny + j));                             /* patch.cpp:1030-1032 */
@@ -664,14 +678,16 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
                 w0 *= expSafe ? exp_table(x0, tabA) : exp_nonpos(x0);
             }
             if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
-                const int rofs0 = ri0.x + (ri0.y ? refCols : 0) + pxr + rc.selx;
+                const int rofs0 = lds_s32(riA + 8u * j) + (sel ? refCols : 0) + pxr + rc.selx;
                 w0 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs0) * gradW));
             }
             w0 = keep0 ? w0 : 0.0;
             sw += w0;
             fit = fma(w0, s0, fit);
+            T = Tn;
+            qr = qrn;
         }
-#else
+        } else
         for (int j = g; j < jEnd; j += 2 * G) {
             const bool two = j + G < jEnd;
             const int j2 = two ? j + G : j;
@@ -729,7 +745,6 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
             sw += w1;
             fit = fma(w1, s1, fit);
         }
-#endif
     }
     fitOut = warp_sum(fit) * invV;
     swOut = warp_sum(sw);
