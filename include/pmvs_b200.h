@@ -188,6 +188,12 @@ int pmvs_pyramid_levels(int cols, int rows, double lodRatio, int cfgMaxLOD, int 
 int pmvs_build_pyramid(int device, const uint8_t *grey0, int cols, int rows, int64_t pitch, double lodRatio, int maxLOD,
                        int withEdge, PmvsLevelOut *levels);
 
+/* The pair scan of the PCMVS neighbour filter, MVS::neighborPatchFiltering (TMVS/mvs/mvs.cpp:448-525), on `device`:
+ * counts[k] = #{ j != first+k : cv::norm(center[first+k] - center[j]) <= radius }, k in [0, count) — the length of the
+ * reference's PatchNeighbor::nid list (:489-499), bit-exact. centers: n x 3 f64 (host); [first, first+count) is the
+ * shard of rows this device scans against all n points (rows are independent). */
+int pmvs_neighbor_counts(int device, int n, const double *centers, double radius, int first, int count, int *counts);
+
 /* Upload config + cameras + pyramids to `device` and build the derived tables
  * (distance weighting MVS::initPatchDistanceWeighting mvs.cpp:97-114; lodRatio^l).
  * rngSeed keys the counter-based replacement of the reference's srand(time)+rand()

@@ -55,6 +55,7 @@ def lib():
         L.orc_rand31.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_uint64]
         L.orc_stream_key.restype = C.c_uint64
         L.orc_stream_key.argtypes = [C.c_uint64, C.c_int, C.c_int]
+        L.orc_neighbor_counts.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_int)]
         L.orc_pso_test.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int,
                                    C.POINTER(C.c_double), C.c_uint64, C.c_int, C.POINTER(C.c_double),
                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double)]
@@ -137,3 +138,12 @@ class Oracle:
         mode = self.pso_mode if pso_mode is None else pso_mode
         self.L.orc_refine_batch(self.h, n, patches, out, flags, mode, patch_threads, pso_threads)
         return out
+
+
+def neighbor_counts(centers, radius):
+    """orc_neighbor_counts: centers [n,3] float64 -> int32 [n] (mvs.cpp:470-499)."""
+    import numpy as np
+    c = np.ascontiguousarray(centers, dtype=np.float64)
+    out = np.zeros(len(c), dtype=np.int32)
+    lib().orc_neighbor_counts(len(c), c.ctypes.data_as(C.POINTER(C.c_double)), float(radius), out.ctypes.data_as(C.POINTER(C.c_int)))
+    return out

@@ -1093,6 +1093,26 @@ void orc_pso_test(int fnId, const double *L, const double *U, int maxIter, int P
             q[6] = p.fitness; q[7] = p.pBestFitness;
         }
 }
+/* MVS::neighborPatchFiltering's per-patch neighbour list length (TMVS/mvs/mvs.cpp:470-499): the reference builds the
+ * list of all other patches with dist = cv::norm(center - centerN) (:483), sorts it ascending and keeps entries until
+ * dist > neighborRadius (:496); the length equals the number of j != i with dist <= radius. cv::norm(Vec3d) is
+ * sqrt(x*x + y*y + z*z) accumulated left to right (compiled here with -ffp-contract=off). */
+void orc_neighbor_counts(int n, const double *centers, double radius, int *counts) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+        int c = 0;
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            const double dx = centers[3 * i] - centers[3 * j], dy = centers[3 * i + 1] - centers[3 * j + 1], dz = centers[3 * i + 2] - centers[3 * j + 2];
+            double s = dx * dx;
+            s += dy * dy;
+            s += dz * dz;
+            const double dist = sqrt(s);
+            if (!(dist > radius)) ++c;       /* :496 breaks on dist > radius */
+        }
+        counts[i] = c;
+    }
+}
 double orc_test_fn(int fnId, const double *x) { return testFn(x, &fnId); }
 void *orc_test_fn_ptr(void) { return (void *)testFn; }
 

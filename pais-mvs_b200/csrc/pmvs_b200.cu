@@ -19,6 +19,7 @@
 
 #include "pmvs_patch.cuh"
 #include "pmvs_pyramid.cuh"
+#include "pmvs_filter.cuh"
 
 #define PMVS_VERSION "pmvs_b200 0.1 (sm_100a)"
 /* the alternative register budget of refine_kernel: __launch_bounds__(PMVS_ALT_T, PMVS_ALT_B) (160 x 4 = 96 registers) */
@@ -789,6 +790,31 @@ int pmvs_build_pyramid(int device, const uint8_t *grey0, int cols, int rows, int
     cudaFree(dEdge);
     cudaStreamDestroy(st);
     if (rc != PMVS_OK) return rc;
+    return e == cudaSuccess ? PMVS_OK : (e == cudaErrorMemoryAllocation ? PMVS_E_NOMEM : PMVS_E_CUDA);
+}
+
+int pmvs_neighbor_counts(int device, int n, const double *centers, double radius, int first, int count, int *counts) {
+    if (n < 0 || first < 0 || count < 0 || first + (long long)count > n || (n > 0 && !centers) || (count > 0 && !counts)) return PMVS_E_ARG;
+    if (count == 0) return PMVS_OK;
+    int devs = 0;
+    if (cudaGetDeviceCount(&devs) != cudaSuccess || device < 0 || device >= devs) return PMVS_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return PMVS_E_CUDA;
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return PMVS_E_CUDA;
+    double *dC = nullptr;
+    int *dN = nullptr;
+    cudaError_t e = cudaMalloc(&dC, sizeof(double) * 3 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&dN, sizeof(int) * (size_t)count);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dC, centers, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        neighbor_count_kernel<<<(count + PMVS_NB_TILE - 1) / PMVS_NB_TILE, PMVS_NB_TILE, 0, st>>>(n, dC, radius, first, count, dN);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, dN, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dC);
+    cudaFree(dN);
+    cudaStreamDestroy(st);
     return e == cudaSuccess ? PMVS_OK : (e == cudaErrorMemoryAllocation ? PMVS_E_NOMEM : PMVS_E_CUDA);
 }
 

@@ -1,8 +1,8 @@
 /*
  * tmvs — command-line driver: `tmvs -r <file.nvm|.nvm2|.mvs>` is the reference's `TMVS.exe -r` (TMVS/TMVS.cpp:76-122,
  * :174-203): compiled defaults -> config.txt -> load -> config.txt again -> init.mvs -> seed refinement -> seed.mvs ->
- * expansion -> exp.mvs / exp.ply / exp.psr, total time printed as "time1". The other reference commands (-f filters,
- * -v / -a viewer) are outside this repository's scope.
+ * expansion -> exp.mvs / exp.ply / exp.psr, total time printed as "time1". `tmvs -f <file.mvs>` is `TMVS.exe -f`
+ * (TMVS.cpp:124-170). The viewer commands (-v / -a) are outside this repository's scope.
  *
  * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
  * round, default 1024), --device D, --gpus N (shard every batch over N GPUs), --seed S (run seed of the counter-based PSO
@@ -29,6 +29,38 @@ static bool loadAny(MVS &mvs, const std::string &file) {
     return false;
 }
 
+/* `tmvs -f file.mvs`, TMVS.cpp:124-170: PMVS cell / visibility / neighbour-cell filters, then the PCMVS neighbour
+ * filter (its pair scan on the GPU), writing the reference's eight output files. */
+static int runFiltering(MVS &mvs, const std::string &file, const std::string &outDir) {
+    const size_t dot = file.find_last_of('.');
+    if (dot == std::string::npos || file.substr(dot + 1) != "mvs") {
+        printf("filtering only mvs file\n");
+        return 1;
+    }
+    printf("patches: %zu\n", mvs.patches.size());
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    mvs.cellFiltering();
+    mvs.writeMVS((outDir + "PMVS_filter1.mvs").c_str());
+    mvs.writePLY((outDir + "PMVS_filter1.ply").c_str());
+    mvs.visibilityFiltering();
+    mvs.writeMVS((outDir + "PMVS_filter2.mvs").c_str());
+    mvs.writePLY((outDir + "PMVS_filter2.ply").c_str());
+    mvs.neighborCellFiltering(0.25);
+    mvs.writeMVS((outDir + "PMVS_filter3.mvs").c_str());
+    mvs.writePLY((outDir + "PMVS_filter3.ply").c_str());
+    mvs.writeDeletedPatchMVS((outDir + "PMVS_filter_deleted.mvs").c_str());
+    mvs.writeDeletedPatchPLY((outDir + "PMVS_filter_deleted.ply").c_str());
+    mvs.clearDeletedPatches();
+    if (!mvs.neighborPatchFiltering(0.25)) { fprintf(stderr, "PCMVS filter failed: %s\n", mvs.lastError().c_str()); return 1; }
+    mvs.writeMVS((outDir + "PCMVS_filter.mvs").c_str());
+    mvs.writePLY((outDir + "PCMVS_filter.ply").c_str());
+    mvs.writeDeletedPatchMVS((outDir + "PCMVS_filter_deleted.mvs").c_str());
+    mvs.writeDeletedPatchPLY((outDir + "PCMVS_filter_deleted.ply").c_str());
+    printf("patches kept: %zu\n", mvs.patches.size());
+    printf("time1\t%f\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::string mode, input, configFile = "config.txt", outDir, imageDir, convertOut;
     int roundSize = 1024, device = 0, gpus = 1;
@@ -52,11 +84,12 @@ int main(int argc, char **argv) {
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     if (mode.empty()) {   /* TMVS.cpp:183-197 */
+        printf("usage: tmvs -f <input.mvs> [--config config.txt] [--out-dir DIR] [--device D] [--gpus N]\n");
         printf("usage: tmvs -r <input.nvm|input.nvm2|input.mvs> [--config config.txt] [--out-dir DIR] [--round K] [--device D] [--gpus N] [--seed S]\n");
         return 2;
     }
-    if (mode == "-f" || mode == "-v" || mode == "-a") {
-        fprintf(stderr, "%s is outside the scope of this build (reconstruction path only)\n", mode.c_str());
+    if (mode == "-v" || mode == "-a") {
+        fprintf(stderr, "%s is outside the scope of this build (reconstruction and filtering only)\n", mode.c_str());
         return 2;
     }
     if (!outDir.empty() && outDir[outDir.size() - 1] != '/') outDir += "/";
@@ -79,6 +112,7 @@ int main(int argc, char **argv) {
     mvs.setConfig(config);
     printf("cameras: %zu patches: %zu\n", mvs.cameras.size(), mvs.patches.size());
     if (mode == "--convert") return mvs.writeMVS(convertOut.c_str()) ? 0 : 1;
+    if (mode == "-f") return runFiltering(mvs, input, outDir);
     if (mvs.patches.empty()) {
         fprintf(stderr, "no seed points in the input (SIFT seed generation, featuremanager.cpp, is out of scope)\n");
         return 1;

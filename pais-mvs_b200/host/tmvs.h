@@ -105,6 +105,17 @@ public:
     bool refineSeedPatches();                                       /* mvs.cpp:196-231 */
     bool expansionPatches();                                        /* mvs.cpp:233-275, in rounds */
 
+    /* `-f` post-process (TMVS.cpp:124-170). The three PMVS filters are the reference's serial cell-map walks; the
+     * PCMVS filter's O(N^2) pair scan runs on the GPU(s) (pmvs_neighbor_counts), rows sharded over numGpus devices. */
+    void cellFiltering();                                           /* mvs.cpp:279-325 */
+    void visibilityFiltering();                                     /* mvs.cpp:399-446 */
+    void neighborCellFiltering(double neighborRatio);               /* mvs.cpp:327-397 */
+    bool neighborPatchFiltering(double neighborRatio);              /* mvs.cpp:448-525 */
+    bool writeDeletedPatchMVS(const char *fileName) const;          /* filewriter.cpp:173-204 */
+    bool writeDeletedPatchPLY(const char *fileName) const;          /* filewriter.cpp:206-241 */
+    void clearDeletedPatches() { deletedPatches.clear(); }          /* mvs.cpp:154-156 */
+    double lastAvgNeighborNum = 0;                                  /* "average neighbor number", mvs.cpp:506-511 */
+
     /* pieces exposed for tests */
     bool addCamera(Camera &cam, bool loadImage);
     void reCentering();                                             /* mvs.cpp:135-145, patch.cpp:67-112 */
@@ -127,6 +138,7 @@ private:
     std::string err;
     bool ensureContext();
     void setCellMaps();                                             /* mvs.cpp:116-133 */
+    void ensureFilterMaps();                                        /* the `if (cellMaps.empty())` prologue of every filter */
     void insertPatch(const Patch &p);                               /* mvs.cpp:579-601 */
     void deletePatch(int id);                                       /* mvs.cpp:607-634 */
     bool refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::vector<std::vector<int> > *parentCams);

@@ -747,6 +747,195 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
 }
 
 /* ---------------------------------------------------------------------------------------------------------
+ * `-f` filters (mvs.cpp:279-525)
+ * ------------------------------------------------------------------------------------------------------- */
+void MVS::ensureFilterMaps() {   /* mvs.cpp:280-283, :328-331, :400-403, :449-452 */
+    if (cellMaps.empty()) {
+        setNeighborRadius();
+        setCellMaps();
+    }
+}
+
+void MVS::cellFiltering() {   /* mvs.cpp:279-325 */
+    ensureFilterMaps();
+    for (size_t i = 0; i < cameras.size(); ++i) {
+        CellMap &map = cellMaps[i];
+        for (int x = 0; x < map.width; ++x)
+            for (int y = 0; y < map.height; ++y) {
+                const std::vector<int> &cell = map.cell(x, y);
+                const int pthNum = (int)cell.size();
+                std::vector<int> removeIdx;
+                for (int j = 0; j < pthNum; ++j) {
+                    double corrSum = 0;
+                    for (int k = 0; k < pthNum; ++k) {
+                        if (j == k) continue;
+                        std::map<int, Patch>::const_iterator pk = patches.find(cell[k]);
+                        if (pk == patches.end()) continue;
+                        corrSum += pk->second.correlation;
+                    }
+                    std::map<int, Patch>::const_iterator pj = patches.find(cell[j]);
+                    if (pj == patches.end()) continue;
+                    if (pj->second.correlation * (double)pj->second.camIdx.size() < corrSum) removeIdx.push_back(cell[j]);
+                }
+                for (size_t j = 0; j < removeIdx.size(); ++j) deletePatch(removeIdx[j]);
+            }
+    }
+}
+
+void MVS::neighborCellFiltering(double neighborRatio) {   /* mvs.cpp:327-397 */
+    ensureFilterMaps();
+    for (size_t i = 0; i < cameras.size(); ++i) {
+        CellMap &map = cellMaps[i];
+        for (int x = 0; x < map.width; ++x)
+            for (int y = 0; y < map.height; ++y) {
+                const std::vector<int> &cell = map.cell(x, y);
+                std::vector<int> removeIdx;
+                const int nx[9] = {x, x - 1, x + 1, x - 1, x + 1, x + 1, x, x - 1, x};
+                const int ny[9] = {y, y - 1, y - 1, y + 1, y + 1, y, y + 1, y, y - 1};
+                const int pthNum = (int)cell.size();
+                for (int j = 0; j < pthNum; ++j) {
+                    std::map<int, Patch>::const_iterator pc = patches.find(cell[j]);
+                    if (pc == patches.end()) continue;
+                    const Patch &centerPth = pc->second;
+                    int neighborPthSum = 0, neighborPthNum = 0;
+                    for (int q = 0; q < 9; ++q) {
+                        if (!map.inMap(nx[q], ny[q])) continue;
+                        const std::vector<int> &neighborCell = map.cell(nx[q], ny[q]);
+                        neighborPthSum += (int)neighborCell.size();
+                        for (size_t k = 0; k < neighborCell.size(); ++k) {
+                            std::map<int, Patch>::const_iterator pn = patches.find(neighborCell[k]);
+                            if (pn == patches.end()) continue;
+                            if (isNeighbor(centerPth, pn->second, cfg.neighborRadius)) ++neighborPthNum;
+                        }
+                    }
+                    if ((double)neighborPthNum / (double)neighborPthSum < neighborRatio) removeIdx.push_back(centerPth.id);
+                }
+                for (size_t k = 0; k < removeIdx.size(); ++k) deletePatch(removeIdx[k]);
+            }
+    }
+}
+
+void MVS::visibilityFiltering() {   /* mvs.cpp:399-446 */
+    ensureFilterMaps();
+    for (std::map<int, Patch>::iterator it = patches.begin(); it != patches.end();) {
+        const Patch &pth = it->second;
+        const int camNum = (int)pth.camIdx.size();
+        int visibleCount = camNum;
+        for (int i = 0; i < camNum && 2 * (size_t)i + 1 < pth.imgPoint.size(); ++i) {
+            const Camera &cam = cameras[pth.camIdx[i]];
+            const double d[3] = {pth.center[0] - cam.center[0], pth.center[1] - cam.center[1], pth.center[2] - cam.center[2]};
+            const double depth = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);                  /* cv::norm */
+            const int cx = (int)(pth.imgPoint[2 * i] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * i + 1] / cfg.cellSize);
+            const CellMap &map = cellMaps[pth.camIdx[i]];
+            if (!map.inMap(cx, cy)) continue;          /* the reference indexes the cell unchecked (out of range there is undefined) */
+            const std::vector<int> &cell = map.cell(cx, cy);
+            for (size_t p = 0; p < cell.size(); ++p) {
+                if (cell[p] == pth.id) continue;
+                std::map<int, Patch>::const_iterator pn = patches.find(cell[p]);
+                if (pn == patches.end()) continue;
+                const double e[3] = {pn->second.center[0] - cam.center[0], pn->second.center[1] - cam.center[1], pn->second.center[2] - cam.center[2]};
+                const double neighborDepth = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+                if (depth > neighborDepth) { --visibleCount; break; }
+            }
+        }
+        if (visibleCount < cfg.minCamNum) {
+            const int id = pth.id;
+            ++it;                                   /* std::map::erase only invalidates the erased element */
+            deletePatch(id);
+            continue;
+        }
+        ++it;
+    }
+}
+
+bool MVS::neighborPatchFiltering(double neighborRatio) {   /* mvs.cpp:448-525 */
+    ensureFilterMaps();
+    const int n = (int)patches.size();
+    if (n == 0) return true;
+    std::vector<int> ids;
+    std::vector<double> centers;
+    ids.reserve(n);
+    centers.reserve(3 * (size_t)n);
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) {
+        ids.push_back(it->first);
+        centers.insert(centers.end(), it->second.center, it->second.center + 3);
+    }
+    /* the reference's per-patch distance list + sort + radius cut (:470-499) only feeds a count: one GPU pair scan,
+     * rows sharded over the devices (independent units, no exchange) */
+    std::vector<int> counts((size_t)n, 0);
+    const int G = numGpus > 0 ? numGpus : 1;
+    std::vector<int> rc((size_t)G, PMVS_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        const int base = n / G, extra = n % G;
+        const int first = g * base + std::min(g, extra), count = base + (g < extra ? 1 : 0);
+        th.emplace_back([&, g, first, count]() {
+            rc[g] = pmvs_neighbor_counts(device + g, n, centers.data(), cfg.neighborRadius, first, count, counts.data() + first);
+        });
+    }
+    for (size_t g = 0; g < th.size(); ++g) th[g].join();
+    for (int g = 0; g < G; ++g)
+        if (rc[g] != PMVS_OK) { err = "pmvs_neighbor_counts failed (no CUDA device? there is no CPU path)"; return false; }
+    double avg = 0;                                                  /* :502-506 */
+    for (int i = 0; i < n; ++i) avg += (double)counts[i];
+    avg /= (double)n;
+    lastAvgNeighborNum = avg;
+    printf("\naverage neighbor number: %f\n", avg);
+    /* the reference pushes PatchNeighbor records from OpenMP threads (:497-501), so its deletion order — and with it
+     * the order of deletedPatches — is nondeterministic; the SET removed is not. Here: ascending id. */
+    for (int i = 0; i < n; ++i)
+        if ((double)counts[i] < avg * neighborRatio) deletePatch(ids[i]);
+    return true;
+}
+
+static void writePatchRecord(std::ofstream &file, const Patch &p) {   /* filewriter.cpp:49-69 */
+    const int camNum = (int)p.camIdx.size();
+    file.write((const char *)p.center, 3 * sizeof(double));
+    file.write((const char *)p.normalS, 2 * sizeof(double));
+    file.write((const char *)&camNum, sizeof(int));
+    for (int k = 0; k < camNum; ++k) file.write((const char *)&p.camIdx[k], sizeof(int));
+    file.write((const char *)&p.fitness, sizeof(double));
+    file.write((const char *)&p.correlation, sizeof(double));
+}
+
+bool MVS::writeDeletedPatchMVS(const char *fileName) const {   /* filewriter.cpp:173-204 */
+    std::ofstream file(fileName, std::ios::binary);
+    if (!file.is_open()) return false;
+    file << "MVS_V3" << "\n";
+    file.write((const char *)&cfg, sizeof(MvsConfig));
+    file << "CAMERAS " << (int)cameras.size() << "\n";
+    for (size_t i = 0; i < cameras.size(); ++i) {
+        const Camera &c = cameras[i];
+        const int len = (int)c.fileName.size();
+        file.write((const char *)&len, sizeof(int));
+        file.write(c.fileName.data(), len);
+        file.write((const char *)c.center, 3 * sizeof(double));
+        file.write((const char *)c.focal, 2 * sizeof(double));
+        file.write((const char *)c.principal, 2 * sizeof(double));
+        file.write((const char *)c.quaternion, 4 * sizeof(double));
+        file.write((const char *)&c.radialDistortion, sizeof(double));
+    }
+    file << "PATCHES " << (int)deletedPatches.size() << "\n";
+    for (size_t i = 0; i < deletedPatches.size(); ++i) writePatchRecord(file, deletedPatches[i]);
+    return (bool)file;
+}
+
+bool MVS::writeDeletedPatchPLY(const char *fileName) const {   /* filewriter.cpp:206-241 */
+    std::ofstream file(fileName);
+    if (!file.is_open()) return false;
+    file << "ply\nformat ascii 1.0\nelement vertex " << deletedPatches.size() << "\n";
+    file << "property float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n";
+    file << "property uchar diffuse_red\nproperty uchar diffuse_green\nproperty uchar diffuse_blue\nend_header\n";
+    for (size_t i = 0; i < deletedPatches.size(); ++i) {
+        const Patch &p = deletedPatches[i];
+        file << p.center[0] << " " << p.center[1] << " " << p.center[2] << " ";
+        file << p.normal[0] << " " << p.normal[1] << " " << p.normal[2] << " ";
+        file << int(p.color[2]) << " " << int(p.color[1]) << " " << int(p.color[0]) << "\n";
+    }
+    return (bool)file;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
  * loaders / writers
  * ------------------------------------------------------------------------------------------------------- */
 static std::string dirOf(const char *fileName) {   /* FileLoader::getDir, fileloader.cpp:9-13 */

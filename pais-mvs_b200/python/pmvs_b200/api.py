@@ -127,3 +127,18 @@ def build_pyramid(grey0, lod_ratio, cfg_max_lod, with_edge=True, device=0):
     if rc != 0:
         raise PmvsError(rc, "pmvs_build_pyramid failed")
     return out
+
+
+def neighbor_counts(centers, radius, device=0, first=0, count=None):
+    """The PCMVS neighbour filter's pair scan (MVS::neighborPatchFiltering, mvs.cpp:470-499) on the GPU: for the rows
+    [first, first+count) of centers [n,3] f64, the number of OTHER points within `radius` (norm <= radius). int32."""
+    import numpy as np
+    L = load()
+    c = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+    n = len(c)
+    count = n - first if count is None else count
+    out = np.zeros(max(count, 0), dtype=np.int32)
+    rc = L.pmvs_neighbor_counts(device, n, c.ctypes.data, float(radius), first, count, out.ctypes.data)
+    if rc != 0:
+        raise PmvsError(rc, "pmvs_neighbor_counts failed")
+    return out

@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG_ROOT, "csrc")
 # every symbol include/pmvs_b200.h declares
 SYMBOLS = ["pmvs_create", "pmvs_set_neighbor_radius", "pmvs_set_config", "pmvs_fitness_batch", "pmvs_refine_batch",
            "pmvs_refine_batch_device", "pmvs_launch_count", "pmvs_pso_test", "pmvs_destroy", "pmvs_last_error",
-           "pmvs_version", "pmvs_pyramid_levels", "pmvs_build_pyramid"]
+           "pmvs_version", "pmvs_pyramid_levels", "pmvs_build_pyramid", "pmvs_neighbor_counts"]
 
 _LIB = None
 
@@ -66,6 +66,8 @@ def load():
     L.pmvs_version.restype = C.c_char_p
     L.pmvs_pyramid_levels.restype = C.c_int
     L.pmvs_pyramid_levels.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.pmvs_neighbor_counts.restype = C.c_int
+    L.pmvs_neighbor_counts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p]
     L.pmvs_build_pyramid.restype = C.c_int
     L.pmvs_build_pyramid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_int,
                                      C.POINTER(abi.PmvsLevelOut)]

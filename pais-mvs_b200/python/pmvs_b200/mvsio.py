@@ -97,6 +97,25 @@ def read_mvs(path):
     return cfg, cams, patches
 
 
+def write_mvs(path, cfg, cams, patches):
+    """MVS_V3 writer (TMVS/io/filewriter.cpp:26-102): cams = scene.Camera objects (image name `name`.pgm), patches = dicts
+    with center, normalS, camIdx, fitness, correlation."""
+    with open(path, "wb") as f:
+        f.write(b"MVS_V3\n")
+        f.write(bytes(cfg))
+        f.write(b"CAMERAS %d\n" % len(cams))
+        for c in cams:
+            name = (c.name + ".pgm").encode()
+            f.write(struct.pack("<i", len(name)) + name)
+            f.write(struct.pack("<12d", *c.center, *c.focal, *c.principal, *c.quaternion, 0.0))
+        f.write(b"PATCHES %d\n" % len(patches))
+        for p in patches:
+            f.write(struct.pack("<5d", *p["center"], *p["normalS"]))
+            f.write(struct.pack("<i", len(p["camIdx"])))
+            f.write(struct.pack("<%di" % len(p["camIdx"]), *p["camIdx"]))
+            f.write(struct.pack("<2d", p["fitness"], p["correlation"]))
+
+
 def read_ply(path):
     lines = open(path).read().split("\n")
     n = int([l for l in lines if l.startswith("element vertex")][0].split()[-1])

@@ -64,5 +64,7 @@ def test_nvm2_and_defaults(tmvs_bin, tmp_path, small_scene):
 
 def test_usage_and_out_of_scope_commands(tmvs_bin):
     assert subprocess.run([tmvs_bin], capture_output=True).returncode == 2
-    r = subprocess.run([tmvs_bin, "-f", "x.mvs"], capture_output=True, text=True)
+    r = subprocess.run([tmvs_bin, "-v", "x.mvs"], capture_output=True, text=True)        # viewer: out of scope
     assert r.returncode == 2 and "scope" in r.stderr
+    r = subprocess.run([tmvs_bin, "-f", "missing.mvs"], capture_output=True, text=True)  # filtering: in scope, file missing
+    assert r.returncode == 1 and "load failed" in r.stderr
