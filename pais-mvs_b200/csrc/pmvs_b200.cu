@@ -28,7 +28,7 @@
 #define PMVS_ALT_B 4
 #endif
 #ifndef PMVS_DEFAULT_LEAN
-#define PMVS_DEFAULT_LEAN false
+#define PMVS_DEFAULT_LEAN true
 #endif
 
 /* ======================================================================================================= */
@@ -61,7 +61,7 @@ static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t he
     pl.distOff = off;
     off += sizeof(double) * ((size_t)PMVS_DIST_PAD(ps) + 64);     /* distance weights + exp table */
     pl.warpOff = off;
-    pl.perWarp = (((size_t)vcap * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_COLV_DOUBLES(vcap, ps);
+    pl.perWarp = (((size_t)PMVS_HCAP(vcap) * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_HYP_DOUBLES + PMVS_COLV_DOUBLES(vcap, ps);
     off += sizeof(double) * pl.perWarp * nWarps;
     pl.corrOff = off;
     if (withCorr) off += sizeof(double) * (size_t)vcap * vcap;
@@ -88,11 +88,12 @@ __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArg
     double *base = (double *)(smem + a.warpOff) + (size_t)a.perWarp * warp;
     WarpWork W;
     W.H = base;
-    W.xs = base + (size_t)a.vcap * 9;
+    W.xs = base + (size_t)PMVS_HCAP(a.vcap) * 9;
     W.ys = W.xs + a.ps;
     W.colv = base + a.perWarp - PMVS_COLV_DOUBLES(a.vcap, a.ps);
+    W.hyp = W.colv - PMVS_HYP_DOUBLES;
     W.gv = W.colv + PMVS_COLV_SLOTS(a.vcap);
-    W.rowf = W.gv + PMVS_GV_DOUBLES * 16;
+    W.rowf = W.gv + PMVS_GV_DOUBLES * PMVS_COLV_VIEWS(a.vcap);
     W.rowi = (int2 *)(W.rowf + PMVS_PS_PAD(a.ps));
     return W;
 }
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(128) fitness_batch_kernel(const __grid_constan
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     double *sDistW = (double *)(smem + a.distOff);
-    for (int k = tid; k < a.ps * a.ps; k += blockDim.x) sDistW[k] = S.distW[k];
+    for (int k = tid; k < a.ps * a.ps && !PMVS_DIST_GLOBAL; k += blockDim.x) sDistW[k] = S.distW[k];
     load_exp_table(sDistW, a.ps, tid, blockDim.x);
     /* one EvalCtx + view table per warp: ctaOff holds NW contexts, viewOff NW*vcap views */
     EvalCtx &E = ((FitWarpS *)(smem + a.ctaOff))[warp].E;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
     CtaS &c = *(CtaS *)(smem + a.ctaOff);
     double *sDistW = (double *)(smem + a.distOff);
     double *corr = (double *)(smem + a.corrOff);
-    for (int k = tid; k < a.ps * a.ps; k += blockDim.x) sDistW[k] = S.distW[k];
+    for (int k = tid; k < a.ps * a.ps && !PMVS_DIST_GLOBAL; k += blockDim.x) sDistW[k] = S.distW[k];
     load_exp_table(sDistW, a.ps, tid, blockDim.x);
     if (tid == 0) {
         c.E.view = (ViewS *)(smem + a.viewOff);
@@ -254,6 +255,9 @@ struct TestEval {
         case 3: return (x[0] > 0.5) ? DBL_MAX : fabs(x[0]) + fabs(x[1]) + fabs(x[2]);
         case 4: return floor(4 * fabs(x[0])) + floor(4 * fabs(x[1])) + floor(4 * fabs(x[2]));
         }
+    }
+    __device__ __forceinline__ void batch(int m, const double *const *pos, double *out) const {
+        for (int k = 0; k < m; ++k) out[k] = (*this)(pos[k]);
     }
 };
 struct PsoTestS {
@@ -681,10 +685,12 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
     if (nPart > PMVS_MAX_PARTICLES) nPart = PMVS_MAX_PARTICLES;
     const size_t ctaBytes = ((sizeof(CtaS) + 15) & ~(size_t)15);
     SmemPlan pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, ctaBytes + sizeof(ParticleS) * (size_t)nPart);
-    /* two register budgets of the same kernel: 128 registers (16 warps/SM) or 96 (20 warps/SM, NW <= 5 only) */
+    /* two register budgets of the same kernel: 128 registers (16 warps/SM) or 96 (20 warps/SM, NW <= 5 only). Measured
+     * (8192 patches, P = 15): 3 views 217k vs 199k patches/s and 5 views 142k vs 137k in favour of 96 registers, 8 views
+     * 54.8k vs 57.3k in favour of 128 (the wider view loops spill), 12 views equal. */
     typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *);
     const char *envRegs = getenv("PMVS_REGS");
-    const bool lean = NW <= PMVS_ALT_T / 32 && (envRegs ? atoi(envRegs) != 128 : PMVS_DEFAULT_LEAN);
+    const bool lean = NW <= PMVS_ALT_T / 32 && (envRegs ? atoi(envRegs) != 128 : (PMVS_DEFAULT_LEAN && ctx->vcap <= 6));
     RefineFn fn = lean ? (RefineFn)refine_kernel<PMVS_ALT_T, PMVS_ALT_B> : (RefineFn)refine_kernel<256, 2>;
     const int warpsPerSm = lean ? PMVS_ALT_T * PMVS_ALT_B / 32 : 16;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));

@@ -28,12 +28,23 @@
 #define PMVS_MAX_RADIUS 31
 #define PMVS_MAX_PS (2 * PMVS_MAX_RADIUS + 1)
 #define PMVS_FULL 0xffffffffu
-#define PMVS_COLV_VIEWS(vcap) ((vcap) < 5 ? 5 : ((vcap) > 16 ? 16 : (vcap)))
+/* build switches of the evaluation path (shared memory is taken from L1, which the tap stream lives in: keep it small) */
+#ifndef PMVS_EVAL_BATCH
+#define PMVS_EVAL_BATCH 4       /* hypotheses whose scalar part (homographies ...) one warp computes together; 1 = off */
+#endif
+#ifndef PMVS_DIST_GLOBAL
+#define PMVS_DIST_GLOBAL 1      /* distance weights read through L1 from one global table instead of a copy per CTA */
+#endif
+/* non-reference views with per-lane slots in the column loop (V = 2..16) */
+#define PMVS_COLV_VIEWS(vcap) ((vcap) < 2 ? 1 : ((vcap) > 16 ? 15 : (vcap) - 1))
 #define PMVS_COLV_SLOTS(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
 #define PMVS_GV_DOUBLES 6                    /* per non-reference view: h1, h4, h7, quad pointer, cols, spare */
 #define PMVS_PS_PAD(ps) (((ps) + 1) & ~1)
 /* per-warp area of the column loop: per-lane slots | compact non-reference view table | per-row {fy} | per-row {py*cols, sel} */
-#define PMVS_COLV_DOUBLES(vcap, ps) (PMVS_COLV_SLOTS(vcap) + PMVS_GV_DOUBLES * 16 + 2 * PMVS_PS_PAD(ps))
+#define PMVS_COLV_DOUBLES(vcap, ps) (PMVS_COLV_SLOTS(vcap) + PMVS_GV_DOUBLES * PMVS_COLV_VIEWS(vcap) + 2 * PMVS_PS_PAD(ps))
+/* homographies kept per warp: one hypothesis of vcap views, or a batch of up to 4 hypotheses with batch * V <= 32 */
+#define PMVS_HCAP(vcap) ((PMVS_EVAL_BATCH < 2 || (vcap) > 32) ? (vcap) : (PMVS_EVAL_BATCH * (vcap) < 32 ? PMVS_EVAL_BATCH * (vcap) : 32))
+#define PMVS_HYP_DOUBLES 12
 
 struct DevLevel {
     const uint32_t *quad;
@@ -75,8 +86,9 @@ struct WarpWork {
     double *H;      /* V*9 */
     double *xs;     /* patchSize */
     double *ys;     /* patchSize */
+    double *hyp;    /* PMVS_EVAL_BATCH HypoS records: per-hypothesis results of the batched scalar part */
     double *colv;   /* PMVS_COLV_SLOTS(vcap): per-lane column constants of the unchecked loop */
-    double *gv;     /* PMVS_GV_DOUBLES * 16: compact table of the non-reference views */
+    double *gv;     /* PMVS_GV_DOUBLES * PMVS_COLV_VIEWS(vcap): compact table of the non-reference views */
     double *rowf;   /* PMVS_PS_PAD(ps): fractional part of each window row in the reference view */
     int2 *rowi;     /* PMVS_PS_PAD(ps): {floor(y) * refCols, 2 * (cvRound(y) - floor(y))} per window row */
 };
@@ -314,7 +326,7 @@ __device__ __noinline__ bool fitness_samples(const DevScene &S, const EvalCtx &E
         }
         const double avgSad = sad * invV;
         double weight = 1.0;
-        if (useDist) weight *= sDistW[idx];                                           /* patch.cpp:1030-1032 */
+        if (useDist) weight *= PMVS_DIST_GLOBAL ? __ldg(S.distW + idx) : sDistW[idx];                                           /* patch.cpp:1030-1032 */
         if (useDiff) weight *= exp(-avgSad * avgSad * invDiffW);                      /* patch.cpp:1033-1035 */
         if (useGrad) weight *= exp(-1.0 / (__ldg(E.refEdge + rofs) * gradW));         /* patch.cpp:1036-1038 */
         sw += weight;
@@ -467,7 +479,7 @@ __constant__ double kExpTab64[64] = {
     0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
     0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
-#define PMVS_DIST_PAD(ps) (((ps) * (ps) + 1) & ~1)   /* the table sits behind the distance weights in shared memory */
+#define PMVS_DIST_PAD(ps) (PMVS_DIST_GLOBAL ? 0 : (((ps) * (ps) + 1) & ~1))   /* the table sits behind the distance weights in shared memory */
 __device__ __forceinline__ void load_exp_table(double *sDistW, int ps, int tid, int nthreads) {
     for (int k = tid; k < 64; k += nthreads) sDistW[PMVS_DIST_PAD(ps) + k] = kExpTab64[k];
 }
@@ -672,7 +684,7 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
             column_blend<NG>(T, c);
             const double s0 = sum_abs_dev<V>(c, invV);
             double w0 = 1.0;
-            if (useDist) w0 = lds_f64(distA + 8u * (i * ny + j));                             /* patch.cpp:1030-1032 */
+            if (useDist) w0 = PMVS_DIST_GLOBAL ? __ldg(S.distW + (i * ny + j)) : lds_f64(distA + 8u * (i * ny + j));                             /* patch.cpp:1030-1032 */
             if (useDiff) {                                                                    /* patch.cpp:1033-1035 */
                 const double x0 = s0 * s0 * negK;
                 w0 *= expSafe ? exp_table(x0, tabA) : exp_nonpos(x0);
@@ -725,8 +737,8 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
             keep1 = keep1 && two;
             double w0 = 1.0, w1 = 1.0;
             if (useDist) {                                                                    /* patch.cpp:1030-1032 */
-                w0 = lds_f64(distA + 8u * (i * ny + j));
-                w1 = lds_f64(distA + 8u * (i * ny + j2));
+                w0 = PMVS_DIST_GLOBAL ? __ldg(S.distW + (i * ny + j)) : lds_f64(distA + 8u * (i * ny + j));
+                w1 = PMVS_DIST_GLOBAL ? __ldg(S.distW + (i * ny + j2)) : lds_f64(distA + 8u * (i * ny + j2));
             }
             if (useDiff) {                                                                    /* patch.cpp:1033-1035 */
                 const double x0 = s0 * s0 * negK, x1 = s1 * s1 * negK;
@@ -777,11 +789,66 @@ __device__ __forceinline__ bool fitness_columns_dispatch(int nV, const DevScene 
  * loop with the reference's per-sample test, so the DBL_MAX sentinel is reproduced exactly.
  */
 #define PMVS_EDGE_EPS 1e-6
+/* everything of getFitness after the homographies and the reference projection: window axes, corner test, sample loop */
 template <int VCAP>
-__device__ __noinline__ double warp_fitness(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, double theta,
-                               double phi, double depth) {
+__device__ __noinline__ double warp_window(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, const double *pt) {
     const int lane = threadIdx.x & 31;
     const int radius = S.cfg.patchRadius, ps = S.cfg.patchSize;
+    const int nxy = warp_window_axes(pt, radius, ps, W.xs, W.ys);
+    const int nx = nxy & 0xffff, ny = nxy >> 16;
+
+    /* corner test, lane = (view, corner) */
+    bool inside = true;
+    for (int t = lane; t < 4 * E.V; t += 32) {
+        const int v = t >> 2, cidx = t & 3;
+        const double *H = W.H + 9 * v;
+        const ViewS &vw = E.view[v];
+        const double loX = 2.0 + PMVS_EDGE_EPS, hiX = (double)(vw.cols - 3) - PMVS_EDGE_EPS;
+        const double loY = 2.0 + PMVS_EDGE_EPS, hiY = (double)(vw.rows - 3) - PMVS_EDGE_EPS;
+        const double x = W.xs[(cidx & 1) ? nx - 1 : 0], y = W.ys[(cidx & 2) ? ny - 1 : 0];
+        /* w > 0: lo <= n/w < hi  <=>  lo*w <= n < hi*w; the 1e-6 margin dwarfs the rounding of the products */
+        const double w = H[6] * x + H[7] * y + H[8];
+        const double nxw = H[0] * x + H[1] * y + H[2], nyw = H[3] * x + H[4] * y + H[5];
+        if (!(w > 0.0 && nxw >= loX * w && nxw < hiX * w && nyw >= loY * w && nyw < hiY * w)) inside = false;
+    }
+    inside = __all_sync(PMVS_FULL, inside);
+    double fit, sw;
+    bool ok;
+    if (inside) {
+        ok = true;
+        /* lane-per-column loop: every V in 2..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
+        if (VCAP == 8 && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
+        else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
+        else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    __syncwarp();
+    if (!ok) return DBL_MAX;                                                          /* :999-1002 */
+    return fit / sw;                                                                  /* :1046 */
+}
+__device__ __forceinline__ double warp_window_any(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, const double *pt) {
+    if (E.V <= 8) return warp_window<8>(S, E, sDistW, W, pt);
+    if (E.V <= 16) return warp_window<16>(S, E, sDistW, W, pt);
+    return warp_window<0>(S, E, sDistW, W, pt);
+}
+
+/* the reference-image position of the hypothesis and the tests of patch.cpp:951-962; false = DBL_MAX */
+__device__ __forceinline__ bool ref_window_ok(const DevScene &S, const EvalCtx &E, const double *center, double *pt) {
+    const int radius = S.cfg.patchRadius;
+    project_pt(E.refR, E.refT, E.refFocal, E.refPP, E.sc, center, pt);                /* :951-954 */
+    if (!in_image(pt[0], pt[1], E.refCols, E.refRows)) return false;
+    if (pt[0] - radius < 2 || pt[0] + radius >= E.refCols - 3 || pt[1] - radius < 2 || pt[1] + radius >= E.refRows - 3)
+        return false;                                                                 /* :957-962 */
+    return true;
+}
+
+/*
+ * PAIS::getFitness (patch.cpp:914-1047) for the hypothesis (theta, phi, depth); one warp, result in every lane.
+ * Hypotheses whose window corners all project at least PMVS_EDGE_EPS inside every view take the unchecked loop
+ * (a projective map with w > 0 keeps the window inside the convex hull of its corners); anything else takes the
+ * loop with the reference's per-sample test, so the DBL_MAX sentinel is reproduced exactly.
+ */
+__device__ __noinline__ double warp_fitness_any(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W,
+                                                double theta, double phi, double depth) {
     double n[3];
     spherical2Normal(theta, phi, n);                                                  /* :935-936 */
     if (dot3(n, E.refOptN) > 0) return DBL_MAX;                                       /* :939-941 */
@@ -792,48 +859,78 @@ __device__ __noinline__ double warp_fitness(const DevScene &S, const EvalCtx &E,
     __syncwarp();
     warp_homographies(E, center, n, W.H);                                             /* :947-948 */
     double pt[2];
-    project_pt(E.refR, E.refT, E.refFocal, E.refPP, E.sc, center, pt);                /* :951-954 */
-    if (!in_image(pt[0], pt[1], E.refCols, E.refRows)) return DBL_MAX;
-    if (pt[0] - radius < 2 || pt[0] + radius >= E.refCols - 3 || pt[1] - radius < 2 || pt[1] + radius >= E.refRows - 3)
-        return DBL_MAX;                                                               /* :957-962 */
-    const int nxy = warp_window_axes(pt, radius, ps, W.xs, W.ys);
-    const int nx = nxy & 0xffff, ny = nxy >> 16;
-
-    bool inside = true;
-    for (int v = lane; v < E.V; v += 32) {
-        const double *H = W.H + 9 * v;
-        const ViewS &vw = E.view[v];
-        const double loX = 2.0 + PMVS_EDGE_EPS, hiX = (double)(vw.cols - 3) - PMVS_EDGE_EPS;
-        const double loY = 2.0 + PMVS_EDGE_EPS, hiY = (double)(vw.rows - 3) - PMVS_EDGE_EPS;
-#pragma unroll
-        for (int cidx = 0; cidx < 4; ++cidx) {
-            const double x = W.xs[(cidx & 1) ? nx - 1 : 0], y = W.ys[(cidx & 2) ? ny - 1 : 0];
-            /* w > 0: lo <= n/w < hi  <=>  lo*w <= n < hi*w; the 1e-6 margin dwarfs the rounding of the products */
-            const double w = H[6] * x + H[7] * y + H[8];
-            const double nxw = H[0] * x + H[1] * y + H[2], nyw = H[3] * x + H[4] * y + H[5];
-            if (!(w > 0.0 && nxw >= loX * w && nxw < hiX * w && nyw >= loY * w && nyw < hiY * w)) inside = false;
-        }
-    }
-    inside = __all_sync(PMVS_FULL, inside);
-    double fit, sw;
-    bool ok;
-    if (inside) {
-        ok = true;
-        /* lane-per-column loop: every V in 1..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
-        if (VCAP == 8 && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
-        else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
-        else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
-    } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
-    __syncwarp();
-    if (!ok) return DBL_MAX;                                                          /* :999-1002 */
-    return fit / sw;                                                                  /* :1046 */
+    if (!ref_window_ok(S, E, center, pt)) return DBL_MAX;
+    return warp_window_any(S, E, sDistW, W, pt);
 }
 
-__device__ __forceinline__ double warp_fitness_any(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W,
-                                                   double theta, double phi, double depth) {
-    if (E.V <= 8) return warp_fitness<8>(S, E, sDistW, W, theta, phi, depth);
-    if (E.V <= 16) return warp_fitness<16>(S, E, sDistW, W, theta, phi, depth);
-    return warp_fitness<0>(S, E, sDistW, W, theta, phi, depth);
+/*
+ * The same for m <= PMVS_EVAL_BATCH hypotheses of one patch (the particles a warp evaluates in one generation), with
+ * the scalar part — normal, plane, homographies, reference projection — done ONCE for all of them: lane = (hypothesis,
+ * view), m * V <= 32, instead of m passes that each keep V lanes busy. Per lane the arithmetic is the single-hypothesis
+ * path's, so results are bit-identical. Homographies land in W.H + 9 V k; the window part then runs per hypothesis.
+ */
+struct HypoS {
+    double pt[2];
+    int run, _pad;
+};
+__device__ __noinline__ void warp_fitness_batch(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, int m,
+                                                const double *const *pos, double *out) {
+    const int lane = threadIdx.x & 31;
+    const int V = E.V;
+    if (!E.valid || V < 1 || m * V > 32) {          /* not batchable: one at a time */
+        for (int k = 0; k < m; ++k) out[k] = warp_fitness_any(S, E, sDistW, W, pos[k][0], pos[k][1], pos[k][2]);
+        return;
+    }
+    HypoS *hyp = (HypoS *)W.hyp;
+    __syncwarp();
+    {
+        const int k = lane / V, v = lane - k * V;
+        if (k < m) {
+            double n[3], center[3], pt[2];
+            spherical2Normal(pos[k][0], pos[k][1], n);
+            bool run = !(dot3(n, E.refOptN) > 0);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) center[q] = E.ray[q] * pos[k][2] + E.refC[q];
+            if (run) {
+                const double d = -dot3(center, n);
+                double Mref[9], inv[9];
+                plane_matrix(E.refKR, E.refKT, n, d, E.sc, Mref);
+                inv3(Mref, inv);
+                const ViewS &vw = E.view[v];
+                double *Hi = W.H + 9 * (k * V + v);
+                if (vw.isRef) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) Hi[q] = (q % 4 == 0) ? 1.0 : 0.0;
+                } else {
+                    double M[9];
+                    plane_matrix(vw.KR, vw.KT, n, d, E.sc, M);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            double acc = M[r * 3] * inv[c];
+                            acc += M[r * 3 + 1] * inv[3 + c];
+                            acc += M[r * 3 + 2] * inv[6 + c];
+                            Hi[r * 3 + c] = acc;
+                        }
+                }
+                run = ref_window_ok(S, E, center, pt);
+            }
+            if (v == 0) {
+                hyp[k].pt[0] = pt[0];
+                hyp[k].pt[1] = pt[1];
+                hyp[k].run = run ? 1 : 0;
+            }
+        }
+    }
+    __syncwarp();
+    for (int k = 0; k < m; ++k) {
+        if (!hyp[k].run) { out[k] = DBL_MAX; continue; }
+        WarpWork Wk = W;
+        Wk.H = W.H + 9 * (k * V);
+        const double pt[2] = {hyp[k].pt[0], hyp[k].pt[1]};
+        out[k] = warp_window_any(S, E, sDistW, Wk, pt);
+    }
 }
 
 /* Fill the evaluation context for (refCam, LOD, camIdx[0..V)). Collective over `nthreads` threads with index tid. */
@@ -1063,9 +1160,14 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
         }
     }
     __syncthreads();
-    for (int p = warp; p < P; p += NW) {                              /* initFitness :112-119 */
-        const double f = eval(part[p].pos);
-        if (lane == 0) { part[p].fitness = f; part[p].pbf = f; }
+    for (int p0 = warp; p0 < P; p0 += NW * PMVS_EVAL_BATCH) {         /* initFitness :112-119 */
+        const double *pos[PMVS_EVAL_BATCH];
+        double f[PMVS_EVAL_BATCH];
+        int m = 0;
+        for (int p = p0; p < P && m < PMVS_EVAL_BATCH; p += NW) pos[m++] = part[p].pos;
+        eval.batch(m, pos, f);
+        if (lane == 0)
+            for (int k = 0; k < m; ++k) { part[p0 + k * NW].fitness = f[k]; part[p0 + k * NW].pbf = f[k]; }
     }
     evals += P;
     __syncthreads();
@@ -1109,16 +1211,21 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
         __syncthreads();
         if (it >= ps.maxIter || ps.converged) break;
         pso_apply_moves(ps, part, mv, it);                                               /* moveParticles */
-        for (int p = warp; p < P; p += NW) {                                             /* updateFitness :121-135 */
-            const double f = eval(part[p].pos);
-            if (lane == 0) {
-                ParticleS &q = part[p];
-                q.fitness = f;
-                if (f < q.pbf) {
-                    q.pbf = f;
-                    for (int d = 0; d < 3; ++d) q.pBest[d] = q.pos[d];
+        for (int p0 = warp; p0 < P; p0 += NW * PMVS_EVAL_BATCH) {                        /* updateFitness :121-135 */
+            const double *pos[PMVS_EVAL_BATCH];
+            double f[PMVS_EVAL_BATCH];
+            int m = 0;
+            for (int p = p0; p < P && m < PMVS_EVAL_BATCH; p += NW) pos[m++] = part[p].pos;
+            eval.batch(m, pos, f);
+            if (lane == 0)
+                for (int k = 0; k < m; ++k) {
+                    ParticleS &q = part[p0 + k * NW];
+                    q.fitness = f[k];
+                    if (f[k] < q.pbf) {
+                        q.pbf = f[k];
+                        for (int d = 0; d < 3; ++d) q.pBest[d] = q.pos[d];
+                    }
                 }
-            }
         }
         evals += P;
         __syncthreads();

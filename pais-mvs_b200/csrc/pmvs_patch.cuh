@@ -368,6 +368,15 @@ struct PatchEval {
         if ((threadIdx.x & 31) == 0 && f != DBL_MAX) atomicAdd(windowEvals, 1u);
         return f;
     }
+    /* m <= PMVS_EVAL_BATCH positions of this patch's swarm */
+    __device__ __forceinline__ void batch(int m, const double *const *pos, double *out) const {
+        warp_fitness_batch(S, E, sDistW, W, m, pos, out);
+        if ((threadIdx.x & 31) == 0) {
+            unsigned n = 0;
+            for (int k = 0; k < m; ++k) n += out[k] != DBL_MAX ? 1u : 0u;
+            if (n) atomicAdd(windowEvals, n);
+        }
+    }
 };
 
 /* Patch::psoOptimization, :180-219 */
