@@ -704,6 +704,7 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
     {   /* leave everything the CTAs do not need to L1: the tap stream lives there */
         int pct = (int)((100 * (size_t)perSm * (pl.total + 1024) + 233471) / 233472);
         if (pct > 100) pct = 100;
+        if (const char *envC = getenv("PMVS_CARVEOUT")) pct = atoi(envC);      /* tuning: percent of 228 KB given to shared memory */
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     CK(cudaMemsetAsync(ctx->dCounter, 0, sizeof(int), st));
