@@ -297,7 +297,7 @@ def run_gpu(args):
                              "frac": achieved / peak, "traffic": traffic_per_launch(args, n),
                              "peak_source": peak_src,
                              "alg_bytes_per_eval": bpe, "window_evals_per_launch": wev_per_launch, "kernel_ms": k_ms,
-                             "note": "algorithmic tap-bytes model of SURVEY.md 8(d); the kernel is FP64-pipe bound, see DESIGN.md"}}
+                             "note": "algorithmic tap-bytes model of SURVEY.md 8(d); not HBM-bound: issue slots 49 %, FP64 pipe 32 %, DRAM 1 % of peak — see DESIGN.md section 2"}}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ncpu = args.cpu_patches if args.cpu_patches > 0 else max(cores * 512, 256)     # ~10-20 s of CPU work
