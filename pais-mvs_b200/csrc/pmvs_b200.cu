@@ -667,37 +667,75 @@ int pmvs_fitness_batch(pmvs_ctx *ctx, int n, const PmvsHypothesis *in, double *o
     return PMVS_OK;
 }
 
+/* one launch configuration of refine_kernel: NW warps per CTA on one of the register budgets */
+typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *);
+struct RefineCfg {
+    int NW, perSm;
+    RefineFn fn;
+    SmemPlan pl;
+};
+static int refine_config(pmvs_ctx *ctx, int NW, RefineCfg &c) {
+    int nPart = ctx->cfg.particleNum * 2;
+    if (nPart > PMVS_MAX_PARTICLES) nPart = PMVS_MAX_PARTICLES;
+    const size_t ctaBytes = ((sizeof(CtaS) + 15) & ~(size_t)15);
+    c.NW = NW;
+    c.pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, ctaBytes + sizeof(ParticleS) * (size_t)nPart);
+    /* three register budgets of the same kernel: 96 registers (20 warps/SM, NW <= 5), 128 (16 warps/SM, NW <= 8,
+     * or one 16-warp CTA). Measured (8192 patches, P = 15): 3 views 217k vs 199k patches/s and 5 views 142k vs 137k in
+     * favour of 96 registers, 8 views 54.8k vs 57.3k in favour of 128 (the wider view loops spill), 12 views equal. */
+    const char *envRegs = getenv("PMVS_REGS");
+    const bool lean = NW <= PMVS_ALT_T / 32 && (envRegs ? atoi(envRegs) != 128 : (PMVS_DEFAULT_LEAN && ctx->vcap <= 6));
+    c.fn = lean ? (RefineFn)refine_kernel<PMVS_ALT_T, PMVS_ALT_B> : (NW > 8 ? (RefineFn)refine_kernel<512, 1> : (RefineFn)refine_kernel<256, 2>);
+    const int warpsPerSm = lean ? PMVS_ALT_T * PMVS_ALT_B / 32 : 16;
+    c.perSm = 0;
+    if (c.pl.total > 227 * 1024) return PMVS_OK;          /* does not fit: perSm = 0 */
+    CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.pl.total));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.perSm, c.fn, NW * 32, c.pl.total));
+    if (c.perSm > warpsPerSm / NW) c.perSm = warpsPerSm / NW;
+    return PMVS_OK;
+}
+
 static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatchOut *d_out, uint32_t flags, cudaStream_t st) {
     /* Warps per CTA: the swarm's P particles (2P for seeds) are evaluated in rounds of NW, one warp per particle.
-     * Small CTAs (4..8 warps) leave room for several patches per SM, so one patch's serial phases (swarm bookkeeping,
-     * visibility) overlap another's evaluations; pick the NW that wastes the fewest warp slots in the last round. */
+     * Throughput configuration: small CTAs (4..8 warps) leave room for several patches per SM, so one patch's serial
+     * phases (swarm bookkeeping, visibility) overlap another's evaluations; the NW that wastes the fewest warp slots
+     * in the last round. Latency configurations: a batch that cannot fill the GPU anyway (the host driver's expansion
+     * rounds are bounded by the reconstruction's frontier: a few hundred candidates per call) finishes sooner with
+     * more warps per patch — 8 (two CTAs per SM) or 16 (one) — because a generation then takes fewer evaluation
+     * rounds. Picked per launch by waves x rounds; results do not depend on the choice (tests). */
     const int P = ctx->cfg.particleNum;
     int NW = 4, bestWaste = 1 << 30;
     for (int w = 4; w <= 8; ++w) {
         const int waste = ((P + w - 1) / w) * w - P;
         if (waste < bestWaste) { bestWaste = waste; NW = w; }
     }
-    if (const char *envNw = getenv("PMVS_NW")) {       /* tuning override, 4..8 */
+    RefineCfg cfg;
+    int rc = PMVS_OK;
+    if (const char *envNw = getenv("PMVS_NW")) {       /* tuning override, 4..16 */
         const int w = atoi(envNw);
-        if (w >= 4 && w <= 8) NW = w;
+        if (w >= 4 && w <= 16) NW = w;
+        rc = refine_config(ctx, NW, cfg);
+        if (rc) return rc;
+    } else {
+        rc = refine_config(ctx, NW, cfg);
+        if (rc) return rc;
+        long bestScore = cfg.perSm < 1 ? (1L << 60) : (long)((n + ctx->smCount * cfg.perSm - 1) / (ctx->smCount * cfg.perSm)) * ((P + NW - 1) / NW);
+        const int alt[2] = {8, 16};
+        for (int k = 0; k < 2; ++k) {
+            if (alt[k] <= NW || (alt[k] == 16 && P <= 8)) continue;
+            RefineCfg c2;
+            rc = refine_config(ctx, alt[k], c2);
+            if (rc) return rc;
+            if (c2.perSm < 1) continue;
+            const long score = (long)((n + ctx->smCount * c2.perSm - 1) / (ctx->smCount * c2.perSm)) * ((P + alt[k] - 1) / alt[k]);
+            if (score < bestScore) { bestScore = score; cfg = c2; }
+        }
+        NW = cfg.NW;
     }
-    int nPart = ctx->cfg.particleNum * 2;
-    if (nPart > PMVS_MAX_PARTICLES) nPart = PMVS_MAX_PARTICLES;
-    const size_t ctaBytes = ((sizeof(CtaS) + 15) & ~(size_t)15);
-    SmemPlan pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, ctaBytes + sizeof(ParticleS) * (size_t)nPart);
-    /* two register budgets of the same kernel: 128 registers (16 warps/SM) or 96 (20 warps/SM, NW <= 5 only). Measured
-     * (8192 patches, P = 15): 3 views 217k vs 199k patches/s and 5 views 142k vs 137k in favour of 96 registers, 8 views
-     * 54.8k vs 57.3k in favour of 128 (the wider view loops spill), 12 views equal. */
-    typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *);
-    const char *envRegs = getenv("PMVS_REGS");
-    const bool lean = NW <= PMVS_ALT_T / 32 && (envRegs ? atoi(envRegs) != 128 : (PMVS_DEFAULT_LEAN && ctx->vcap <= 6));
-    RefineFn fn = lean ? (RefineFn)refine_kernel<PMVS_ALT_T, PMVS_ALT_B> : (RefineFn)refine_kernel<256, 2>;
-    const int warpsPerSm = lean ? PMVS_ALT_T * PMVS_ALT_B / 32 : 16;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
-    int perSm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, NW * 32, pl.total));
+    const SmemPlan &pl = cfg.pl;
+    RefineFn fn = cfg.fn;
+    int perSm = cfg.perSm;
     if (perSm < 1) return fail(ctx, PMVS_E_UNSUPPORTED, "refine kernel does not fit on an SM with this configuration");
-    if (perSm > warpsPerSm / NW) perSm = warpsPerSm / NW;
     int grid = ctx->smCount * perSm;
     if (grid > ctx->scratchCtas) grid = ctx->scratchCtas;
     if (grid > n) grid = n;
@@ -712,8 +750,9 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
             if ((size_t)steps[k] * 1024 >= need) { kb = steps[k]; break; }
         int pct = (int)((100 * (size_t)kb * 1024) / 233472);
         if (pct > 100) pct = 100;
-        if (getenv("PMVS_DEBUG")) fprintf(stderr, "refine_launch: NW %d, %zu B of shared memory per CTA, %d CTAs/SM -> carve-out %d KB (%d %%)\n", NW, pl.total, perSm, kb, pct);
+        if (getenv("PMVS_DEBUG")) fprintf(stderr, "refine_launch: n %d NW %d, %zu B of shared memory per CTA, %d CTAs/SM -> carve-out %d KB (%d %%)\n", n, NW, pl.total, perSm, kb, pct);
         if (const char *envC = getenv("PMVS_CARVEOUT")) pct = atoi(envC);      /* tuning: percent of 228 KB given to shared memory */
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     CK(cudaMemsetAsync(ctx->dCounter, 0, sizeof(int), st));

@@ -302,6 +302,30 @@ def test_refine_properties_full_size():
     assert kept > 0.9 * n and checked > 0.5 * n
 
 
+def test_refine_independent_of_launch_configuration(small_scene):
+    """Warps per CTA (latency vs throughput configurations, picked per launch from the batch size), register budget and
+    shared-memory carve-out are scheduling choices: the records must not depend on them."""
+    cfg, sc = small_scene
+    patches = sc.patches(40, seed=9)
+    seeds = sc.patches(6, seed=10, ptype=abi.TYPE_SEED)
+    keys = ("PMVS_NW", "PMVS_REGS", "PMVS_CARVEOUT")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    try:
+        with PatchRefiner(cfg, sc.records, seed=42) as pr:
+            base = bytes(pr.refine(patches, flags=abi.F_POST_REMOVE_INVISIBLE)), bytes(pr.refine(seeds))
+            for env in ({"PMVS_NW": "5"}, {"PMVS_NW": "8"}, {"PMVS_NW": "16"}, {"PMVS_NW": "4", "PMVS_REGS": "128"},
+                        {"PMVS_NW": "5", "PMVS_REGS": "128", "PMVS_CARVEOUT": "100"}):
+                os.environ.update(env)
+                got = bytes(pr.refine(patches, flags=abi.F_POST_REMOVE_INVISIBLE)), bytes(pr.refine(seeds))
+                for k in env:
+                    del os.environ[k]
+                assert got == base, env
+    finally:
+        for k, v in saved.items():
+            if v is not None:
+                os.environ[k] = v
+
+
 def test_pyramid_build_on_device():
     """camera.cpp:63-92 on the GPU: bit-exact against the NumPy restatement (grey levels and f64 edge levels), odd
     sizes included; and a context created from level 0 only evaluates exactly like one given every level."""

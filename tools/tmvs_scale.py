@@ -27,3 +27,9 @@ with tempfile.TemporaryDirectory() as d:
     dt = time.time() - t0
     print(r.stdout[-600:], r.stderr[-400:])
     print("wall %.2f s (incl. image load + pyramid build)" % dt)
+    # the -f post-process on the reconstruction just written
+    t0 = time.time()
+    r = subprocess.run([os.path.join(ROOT, "pais-mvs_b200", "bin", "tmvs"), "-f", os.path.join(d, "exp.mvs"), "--config",
+                        os.path.join(d, "config.txt"), "--out-dir", d], cwd=d, capture_output=True, text=True)
+    print(r.stdout[-300:], r.stderr[-300:])
+    print("tmvs -f wall %.2f s" % (time.time() - t0))
