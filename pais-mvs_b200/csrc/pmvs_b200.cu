@@ -256,8 +256,12 @@ struct TestEval {
         case 4: return floor(4 * fabs(x[0])) + floor(4 * fabs(x[1])) + floor(4 * fabs(x[2]));
         }
     }
-    __device__ __forceinline__ void batch(int m, const double *const *pos, double *out) const {
-        for (int k = 0; k < m; ++k) out[k] = (*this)(pos[k]);
+    __device__ __forceinline__ void batch(int m, ParticleS *part, int p0, int stride) const {
+        for (int k = 0; k < m; ++k) {
+            const double f = (*this)(part[p0 + k * stride].pos);
+            if ((threadIdx.x & 31) == 0) part[p0 + k * stride].fitness = f;
+        }
+        __syncwarp();
     }
 };
 struct PsoTestS {

@@ -447,9 +447,6 @@ __device__ __forceinline__ int2 lds_s32x2(unsigned a) {
 #ifndef PMVS_CVT_MIX
 #define PMVS_CVT_MIX 0
 #endif
-#ifndef PMVS_PIPE_VIEWS
-#define PMVS_PIPE_VIEWS 0       /* up to this many non-reference views: one-row software-pipelined loop (0 = off) */
-#endif
 #ifndef PMVS_TWO_ROW_VIEWS
 #define PMVS_TWO_ROW_VIEWS 4    /* up to this many non-reference views, both rows of a trip are staged together */
 #endif
@@ -663,43 +660,6 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         rc.fx = x - (tx - PMVS_MAGIC_FLOOR);
         rc.selx = rx - pxr;
         const int jEnd = active ? ny : 0;
-        if constexpr (NG <= PMVS_PIPE_VIEWS) {
-        /* software pipeline, one row per trip: the coordinates and tap loads of row j+G are issued while row j is
-         * blended, so a tap word is consumed one trip after its load */
-        ColumnTaps<NG> T;
-        uint32_t qr = 0;
-        if (g < jEnd) {
-            column_coords<NG>(gvA, cvA, 0, lds_f64(ysA + 8u * g), T);
-            qr = __ldg(rc.quad + lds_s32(riA + 8u * g));
-        }
-        for (int j = g; j < jEnd; j += G) {
-            const int jn = j + G < jEnd ? j + G : j;
-            ColumnTaps<NG> Tn;
-            column_coords<NG>(gvA, cvA, 0, lds_f64(ysA + 8u * jn), Tn);
-            const uint32_t qrn = __ldg(rc.quad + lds_s32(riA + 8u * jn));
-            const int sel = lds_s32(riA + 8u * j + 4u);
-            double c[V];
-            const bool keep0 = __byte_perm(qr, 0, 0x4440 + sel + rc.selx) != 0;              /* patch.cpp:986 */
-            c[NG] = ref_blend(rc, qr, lds_f64(rfA + 8u * j));
-            column_blend<NG>(T, c);
-            const double s0 = sum_abs_dev<V>(c, invV);
-            double w0 = 1.0;
-            if (useDist) w0 = PMVS_DIST_GLOBAL ? __ldg(S.distW + (i * ny + j)) : lds_f64(distA + 8u * (i * ny + j));                             /* patch.cpp:1030-1032 */
-            if (useDiff) {                                                                    /* patch.cpp:1033-1035 */
-                const double x0 = s0 * s0 * negK;
-                w0 *= expSafe ? exp_table(x0, tabA) : exp_nonpos(x0);
-            }
-            if (useGrad) {                                                                    /* patch.cpp:1036-1038 */
-                const int rofs0 = lds_s32(riA + 8u * j) + (sel ? refCols : 0) + pxr + rc.selx;
-                w0 *= exp_nonpos(-1.0 / (__ldg(refEdge + rofs0) * gradW));
-            }
-            w0 = keep0 ? w0 : 0.0;
-            sw += w0;
-            fit = fma(w0, s0, fit);
-            T = Tn;
-            qr = qrn;
-        }
-        } else
         for (int j = g; j < jEnd; j += 2 * G) {
             const bool two = j + G < jEnd;
             const int j2 = two ? j + G : j;
@@ -869,28 +829,41 @@ __device__ __noinline__ double warp_fitness_any(const DevScene &S, const EvalCtx
  * view), m * V <= 32, instead of m passes that each keep V lanes busy. Per lane the arithmetic is the single-hypothesis
  * path's, so results are bit-identical. Homographies land in W.H + 9 V k; the window part then runs per hypothesis.
  */
+struct ParticleS {   /* pso/particle.h:5-28 */
+    double pos[3], vec[3], pBest[3], nBest[3], fitness, pbf, _r0, _r1;
+};
 struct HypoS {
     double pt[2];
     int run, _pad;
 };
-__device__ __noinline__ void warp_fitness_batch(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, int m,
-                                                const double *const *pos, double *out) {
+/* hypotheses = positions of the particles part[p0 + k * stride], k < m; each result lands in that particle's `fitness`
+ * (lane 0 writes it; the caller reads it back after a __syncwarp). Returns how many ran a full window. */
+__device__ __noinline__ unsigned warp_fitness_batch(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, int m,
+                                                    ParticleS *part, int p0, int stride) {
     const int lane = threadIdx.x & 31;
     const int V = E.V;
+    unsigned ran = 0;
     if (!E.valid || V < 1 || m * V > 32) {          /* not batchable: one at a time */
-        for (int k = 0; k < m; ++k) out[k] = warp_fitness_any(S, E, sDistW, W, pos[k][0], pos[k][1], pos[k][2]);
-        return;
+        for (int k = 0; k < m; ++k) {
+            ParticleS &q = part[p0 + k * stride];
+            const double f = warp_fitness_any(S, E, sDistW, W, q.pos[0], q.pos[1], q.pos[2]);
+            ran += f != DBL_MAX ? 1u : 0u;
+            if (lane == 0) q.fitness = f;
+        }
+        __syncwarp();
+        return ran;
     }
     HypoS *hyp = (HypoS *)W.hyp;
     __syncwarp();
     {
         const int k = lane / V, v = lane - k * V;
         if (k < m) {
+            const double *pos = part[p0 + k * stride].pos;
             double n[3], center[3], pt[2];
-            spherical2Normal(pos[k][0], pos[k][1], n);
+            spherical2Normal(pos[0], pos[1], n);
             bool run = !(dot3(n, E.refOptN) > 0);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) center[q] = E.ray[q] * pos[k][2] + E.refC[q];
+            for (int q = 0; q < 3; ++q) center[q] = E.ray[q] * pos[2] + E.refC[q];
             if (run) {
                 const double d = -dot3(center, n);
                 double Mref[9], inv[9];
@@ -925,12 +898,18 @@ __device__ __noinline__ void warp_fitness_batch(const DevScene &S, const EvalCtx
     }
     __syncwarp();
     for (int k = 0; k < m; ++k) {
-        if (!hyp[k].run) { out[k] = DBL_MAX; continue; }
-        WarpWork Wk = W;
-        Wk.H = W.H + 9 * (k * V);
-        const double pt[2] = {hyp[k].pt[0], hyp[k].pt[1]};
-        out[k] = warp_window_any(S, E, sDistW, Wk, pt);
+        double f = DBL_MAX;
+        if (hyp[k].run) {
+            WarpWork Wk = W;
+            Wk.H = W.H + 9 * (k * V);
+            const double pt[2] = {hyp[k].pt[0], hyp[k].pt[1]};
+            f = warp_window_any(S, E, sDistW, Wk, pt);
+        }
+        ran += f != DBL_MAX ? 1u : 0u;
+        if (lane == 0) part[p0 + k * stride].fitness = f;
     }
+    __syncwarp();
+    return ran;
 }
 
 /* Fill the evaluation context for (refCam, LOD, camIdx[0..V)). Collective over `nthreads` threads with index tid. */
@@ -1005,9 +984,6 @@ __device__ __forceinline__ void finish_eval_ctx(EvalCtx &E, int tid) {
  * Arithmetic is the reference's expression order without contraction, so given identical fitness values the
  * swarm is bit-identical to the unmodified reference solver (tests/test_pso_kat.py).
  * =================================================================================================== */
-struct ParticleS {   /* pso/particle.h:5-28 */
-    double pos[3], vec[3], pBest[3], nBest[3], fitness, pbf, _r0, _r1;
-};
 struct PsoS {
     double L[3], U[3], inter[3];
     double iw, gBestFitness;
@@ -1161,13 +1137,11 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
     }
     __syncthreads();
     for (int p0 = warp; p0 < P; p0 += NW * PMVS_EVAL_BATCH) {         /* initFitness :112-119 */
-        const double *pos[PMVS_EVAL_BATCH];
-        double f[PMVS_EVAL_BATCH];
-        int m = 0;
-        for (int p = p0; p < P && m < PMVS_EVAL_BATCH; p += NW) pos[m++] = part[p].pos;
-        eval.batch(m, pos, f);
+        int m = (P - p0 + NW - 1) / NW;
+        if (m > PMVS_EVAL_BATCH) m = PMVS_EVAL_BATCH;
+        eval.batch(m, part, p0, NW);                                  /* fitness of part[p0 + k NW], k < m */
         if (lane == 0)
-            for (int k = 0; k < m; ++k) { part[p0 + k * NW].fitness = f[k]; part[p0 + k * NW].pbf = f[k]; }
+            for (int k = 0; k < m; ++k) part[p0 + k * NW].pbf = part[p0 + k * NW].fitness;
     }
     evals += P;
     __syncthreads();
@@ -1212,17 +1186,14 @@ __device__ unsigned pso_run(PsoS &ps, ParticleS *part, MoveS &mv, Eval &eval, co
         if (it >= ps.maxIter || ps.converged) break;
         pso_apply_moves(ps, part, mv, it);                                               /* moveParticles */
         for (int p0 = warp; p0 < P; p0 += NW * PMVS_EVAL_BATCH) {                        /* updateFitness :121-135 */
-            const double *pos[PMVS_EVAL_BATCH];
-            double f[PMVS_EVAL_BATCH];
-            int m = 0;
-            for (int p = p0; p < P && m < PMVS_EVAL_BATCH; p += NW) pos[m++] = part[p].pos;
-            eval.batch(m, pos, f);
+            int m = (P - p0 + NW - 1) / NW;
+            if (m > PMVS_EVAL_BATCH) m = PMVS_EVAL_BATCH;
+            eval.batch(m, part, p0, NW);
             if (lane == 0)
                 for (int k = 0; k < m; ++k) {
                     ParticleS &q = part[p0 + k * NW];
-                    q.fitness = f[k];
-                    if (f[k] < q.pbf) {
-                        q.pbf = f[k];
+                    if (q.fitness < q.pbf) {
+                        q.pbf = q.fitness;
                         for (int d = 0; d < 3; ++d) q.pBest[d] = q.pos[d];
                     }
                 }

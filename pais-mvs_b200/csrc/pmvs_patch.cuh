@@ -368,14 +368,10 @@ struct PatchEval {
         if ((threadIdx.x & 31) == 0 && f != DBL_MAX) atomicAdd(windowEvals, 1u);
         return f;
     }
-    /* m <= PMVS_EVAL_BATCH positions of this patch's swarm */
-    __device__ __forceinline__ void batch(int m, const double *const *pos, double *out) const {
-        warp_fitness_batch(S, E, sDistW, W, m, pos, out);
-        if ((threadIdx.x & 31) == 0) {
-            unsigned n = 0;
-            for (int k = 0; k < m; ++k) n += out[k] != DBL_MAX ? 1u : 0u;
-            if (n) atomicAdd(windowEvals, n);
-        }
+    /* m <= PMVS_EVAL_BATCH particles part[p0 + k stride] of this patch's swarm: fitness stored in the particles */
+    __device__ __forceinline__ void batch(int m, ParticleS *part, int p0, int stride) const {
+        const unsigned ran = warp_fitness_batch(S, E, sDistW, W, m, part, p0, stride);
+        if ((threadIdx.x & 31) == 0 && ran) atomicAdd(windowEvals, ran);
     }
 };
 
