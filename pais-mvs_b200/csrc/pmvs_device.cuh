@@ -722,6 +722,155 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
     swOut = warp_sum(sw);
 }
 
+/*
+ * The same loop for any number of views (V > 16: BASELINE.json's 32- and 64-view configurations). The colours of one
+ * pixel no longer fit in registers and per-lane slots for every view would not fit in shared memory, so a pixel takes
+ * two passes over the views in chunks of four — first the cross-view sum, then, with the mean known, the absolute
+ * deviations (the samples are recomputed: same arithmetic, same values) — and the x-part of each homography row is
+ * formed inline, X = fma(h1, y, fma(h0, x, h2)): the expression the slots hold, so a sample is bit-identical to the
+ * V <= 16 loop's. Two rows per trip share the homography loads. Configuration flags are read per trip (the trip is
+ * tens of chunks long).
+ */
+template <int N>
+__device__ __forceinline__ void direct_coords(unsigned hA, unsigned viewA, int k0, int refV, double x, double y, ColumnTaps<N> &t) {
+    double w[N], r[N], e[N];
+    unsigned h[N], va[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int v = k0 + k + (k0 + k >= refV ? 1 : 0);
+        h[k] = hA + 72u * (unsigned)v;
+        va[k] = viewA + (unsigned)sizeof(ViewS) * (unsigned)v;
+        w[k] = fma(lds_f64(h[k] + 56u), y, fma(lds_f64(h[k] + 48u), x, lds_f64(h[k] + 64u)));
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[k]) : "d"(w[k]));
+#pragma unroll
+    for (int k = 0; k < N; ++k) e[k] = fma(-w[k], r[k], 1.0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) e[k] = fma(e[k], e[k], e[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = fma(r[k], e[k], r[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        t.ix[k] = fma(lds_f64(h[k] + 8u), y, fma(lds_f64(h[k]), x, lds_f64(h[k] + 16u))) * r[k];
+        t.fy[k] = fma(lds_f64(h[k] + 32u), y, fma(lds_f64(h[k] + 24u), x, lds_f64(h[k] + 40u))) * r[k];     /* iy */
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        w[k] = __dadd_rd(t.ix[k], PMVS_MAGIC_FLOOR);
+        r[k] = __dadd_rd(t.fy[k], PMVS_MAGIC_FLOOR);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(va[k] + (unsigned)offsetof(ViewS, quad));
+        const int cols = lds_s32(va[k] + (unsigned)offsetof(ViewS, cols));
+        t.px[k] = __double2loint(w[k]);
+        t.q[k] = __ldg(quad + (__double2loint(r[k]) * cols + t.px[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) t.fy[k] = t.fy[k] - (r[k] - PMVS_MAGIC_FLOOR);
+}
+
+/* PASS 0: sum of the colours of views [k0, k0+N) of both rows; PASS 1: sum of |colour - mean| */
+template <int N, int PASS>
+__device__ __forceinline__ void many_chunk(unsigned hA, unsigned viewA, int k0, int refV, double x, double y0, double y1, double m0,
+                                           double m1, double &a0, double &a1) {
+    ColumnTaps<N> ta, tb;
+    double ca[N], cb[N];
+    direct_coords<N>(hA, viewA, k0, refV, x, y0, ta);
+    direct_coords<N>(hA, viewA, k0, refV, x, y1, tb);
+    column_blend<N>(ta, ca);
+    column_blend<N>(tb, cb);
+    if (PASS == 1) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) { ca[k] = fabs(ca[k] - m0); cb[k] = fabs(cb[k] - m1); }
+    }
+    a0 += tree_sum<N>(ca);
+    a1 += tree_sum<N>(cb);
+}
+
+__device__ __noinline__ void fitness_columns_many(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
+                                                  const double *__restrict__ sExpT, const WarpWork &W, int nx, int ny, double &fitOut,
+                                                  double &swOut) {
+    const int V = E.V, NG = V - 1, refV = E.refView;
+    const int lane = threadIdx.x & 31;
+    const int G = nx <= 16 ? 32 / nx : 1;
+    const unsigned hA = smem_addr(W.H), ysA = smem_addr(W.ys), xsA = smem_addr(W.xs), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
+    const unsigned rfA = smem_addr(W.rowf), riA = smem_addr(W.rowi), tabA = smem_addr(sExpT);
+    const double invV = 1.0 / (double)V;
+    const double negK = S.cfg.adaptiveDifferenceEnable ? -(invV * invV) / S.cfg.diffWeighting : 0.0;
+    const bool expSafe = -(255.0 * 255.0) / S.cfg.diffWeighting >= -700.0;
+    const int refCols = E.refCols;
+    for (int j = lane; j < ny; j += 32) {
+        const double y = W.ys[j];
+        const double ty = __dadd_rd(y, PMVS_MAGIC_FLOOR);
+        const int py = __double2loint(ty);
+        W.rowf[j] = y - (ty - PMVS_MAGIC_FLOOR);
+        W.rowi[j] = make_int2(py * refCols, 2 * (__double2int_rn(y) - py));
+    }
+    __syncwarp();
+    double fit = 0, sw = 0;
+    for (int i0 = 0; i0 < nx; i0 += 32) {
+        const int span = nx - i0 < 32 ? nx - i0 : 32;
+        const int i = i0 + (G > 1 ? lane % nx : lane), g = G > 1 ? lane / nx : 0;
+        const bool active = G > 1 ? g < G : lane < span;
+        const double x = lds_f64(xsA + 8u * (active ? i : i0));
+        RefColumn rc;
+        const double tx = __dadd_rd(x, PMVS_MAGIC_FLOOR);
+        const int pxr = __double2loint(tx), rx = __double2int_rn(x);
+        rc.quad = E.refQuad + pxr;
+        rc.fx = x - (tx - PMVS_MAGIC_FLOOR);
+        rc.selx = rx - pxr;
+        const int jEnd = active ? ny : 0;
+        for (int j = g; j < jEnd; j += 2 * G) {
+            const bool two = j + G < jEnd;
+            const int j2 = two ? j + G : j;
+            const double y0 = lds_f64(ysA + 8u * j), y1 = lds_f64(ysA + 8u * j2);
+            const int2 ri0 = lds_s32x2(riA + 8u * j), ri1 = lds_s32x2(riA + 8u * j2);
+            bool keep0, keep1;
+            const double cr0 = ref_sample(rc, ri0, lds_f64(rfA + 8u * j), keep0);
+            const double cr1 = ref_sample(rc, ri1, lds_f64(rfA + 8u * j2), keep1);
+            double s0 = cr0, s1 = cr1;
+            int k0 = 0;
+#pragma unroll 1
+            for (; k0 + 4 <= NG; k0 += 4) many_chunk<4, 0>(hA, viewA, k0, refV, x, y0, y1, 0.0, 0.0, s0, s1);
+#pragma unroll 1
+            for (; k0 < NG; ++k0) many_chunk<1, 0>(hA, viewA, k0, refV, x, y0, y1, 0.0, 0.0, s0, s1);
+            const double m0 = s0 * invV, m1 = s1 * invV;
+            s0 = fabs(cr0 - m0);
+            s1 = fabs(cr1 - m1);
+#pragma unroll 1
+            for (k0 = 0; k0 + 4 <= NG; k0 += 4) many_chunk<4, 1>(hA, viewA, k0, refV, x, y0, y1, m0, m1, s0, s1);
+#pragma unroll 1
+            for (; k0 < NG; ++k0) many_chunk<1, 1>(hA, viewA, k0, refV, x, y0, y1, m0, m1, s0, s1);
+            keep1 = keep1 && two;
+            double w0 = 1.0, w1 = 1.0;
+            if (S.cfg.adaptiveDistanceEnable) {                                               /* patch.cpp:1030-1032 */
+                w0 = PMVS_DIST_GLOBAL ? __ldg(S.distW + (i * ny + j)) : lds_f64(distA + 8u * (i * ny + j));
+                w1 = PMVS_DIST_GLOBAL ? __ldg(S.distW + (i * ny + j2)) : lds_f64(distA + 8u * (i * ny + j2));
+            }
+            if (S.cfg.adaptiveDifferenceEnable) {                                             /* patch.cpp:1033-1035 */
+                const double x0 = s0 * s0 * negK, x1 = s1 * s1 * negK;
+                if (expSafe) { w0 *= exp_table(x0, tabA); w1 *= exp_table(x1, tabA); }
+                else { w0 *= exp_nonpos(x0); w1 *= exp_nonpos(x1); }
+            }
+            if (S.cfg.adaptiveGradientEnable) {                                               /* patch.cpp:1036-1038 */
+                const int rofs0 = ri0.x + (ri0.y ? refCols : 0) + pxr + rc.selx, rofs1 = ri1.x + (ri1.y ? refCols : 0) + pxr + rc.selx;
+                w0 *= exp_nonpos(-1.0 / (__ldg(E.refEdge + rofs0) * S.cfg.gradientWeighting));
+                w1 *= exp_nonpos(-1.0 / (__ldg(E.refEdge + rofs1) * S.cfg.gradientWeighting));
+            }
+            w0 = keep0 ? w0 : 0.0;
+            w1 = keep1 ? w1 : 0.0;
+            sw += w0;
+            fit = fma(w0, s0, fit);
+            sw += w1;
+            fit = fma(w1, s1, fit);
+        }
+    }
+    fitOut = warp_sum(fit) * invV;
+    swOut = warp_sum(sw);
+}
+
 template <int V>
 __device__ __forceinline__ bool fitness_columns_dispatch(int nV, const DevScene &S, const EvalCtx &E, const double *sDistW,
                                                          const double *sExpT, const WarpWork &W, int nx, int ny, double &fit,
@@ -779,6 +928,7 @@ __device__ __noinline__ double warp_window(const DevScene &S, const EvalCtx &E, 
         /* lane-per-column loop: every V in 2..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
         if (VCAP == 8 && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
         else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
+        else if (VCAP == 0 && nx > 0 && E.refView >= 0) fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     __syncwarp();
