@@ -93,7 +93,7 @@ __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArg
     W.colv = base + a.perWarp - PMVS_COLV_DOUBLES(a.vcap, a.ps);
     W.hyp = W.colv - PMVS_HYP_DOUBLES;
     W.gv = W.colv + PMVS_COLV_SLOTS(a.vcap);
-    W.rowf = W.gv + PMVS_GV_DOUBLES * PMVS_COLV_VIEWS(a.vcap);
+    W.rowf = W.gv + PMVS_GV_DOUBLES_TOTAL(a.vcap);
     W.rowi = (int2 *)(W.rowf + PMVS_PS_PAD(a.ps));
     return W;
 }
@@ -708,32 +708,42 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
      * more warps per patch — 8 (two CTAs per SM) or 16 (one) — because a generation then takes fewer evaluation
      * rounds. Picked per launch by waves x rounds; results do not depend on the choice (tests). */
     const int P = ctx->cfg.particleNum;
-    int NW = 4, bestWaste = 1 << 30;
-    for (int w = 4; w <= 8; ++w) {
-        const int waste = ((P + w - 1) / w) * w - P;
-        if (waste < bestWaste) { bestWaste = waste; NW = w; }
-    }
     RefineCfg cfg;
-    int rc = PMVS_OK;
+    int NW = 0;
     if (const char *envNw = getenv("PMVS_NW")) {       /* tuning override, 4..16 */
-        const int w = atoi(envNw);
-        if (w >= 4 && w <= 16) NW = w;
-        rc = refine_config(ctx, NW, cfg);
+        NW = atoi(envNw);
+        if (NW < 4 || NW > 16) NW = 5;
+        const int rc = refine_config(ctx, NW, cfg);
         if (rc) return rc;
     } else {
-        rc = refine_config(ctx, NW, cfg);
-        if (rc) return rc;
-        long bestScore = cfg.perSm < 1 ? (1L << 60) : (long)((n + ctx->smCount * cfg.perSm - 1) / (ctx->smCount * cfg.perSm)) * ((P + NW - 1) / NW);
-        const int alt[2] = {8, 16};
-        for (int k = 0; k < 2; ++k) {
-            if (alt[k] <= NW || (alt[k] == 16 && P <= 8)) continue;
-            RefineCfg c2;
-            rc = refine_config(ctx, alt[k], c2);
+        /* candidates: useful warps per SM = CTAs/SM x NW x (P / (rounds x NW)) for throughput; waves x rounds for latency */
+        static const int cand[] = {4, 5, 6, 7, 8, 16};
+        RefineCfg all[6];
+        double bestThr = -1;
+        int bestT = -1;
+        for (int k = 0; k < 6; ++k) {
+            all[k].perSm = 0;
+            if (cand[k] == 16 && P <= 8) continue;
+            const int rc = refine_config(ctx, cand[k], all[k]);
             if (rc) return rc;
-            if (c2.perSm < 1) continue;
-            const long score = (long)((n + ctx->smCount * c2.perSm - 1) / (ctx->smCount * c2.perSm)) * ((P + alt[k] - 1) / alt[k]);
-            if (score < bestScore) { bestScore = score; cfg = c2; }
+            if (all[k].perSm < 1) continue;
+            const int rounds = (P + cand[k] - 1) / cand[k];
+            /* one CTA per SM leaves a patch's serial phases (swarm bookkeeping, visibility) uncovered */
+            const double thr = (double)all[k].perSm * P / rounds * (all[k].perSm == 1 ? 0.85 : 1.0);
+            if (thr > bestThr + 1e-9 || (thr > bestThr - 1e-9 && bestT >= 0 && rounds < (P + cand[bestT] - 1) / cand[bestT])) { bestThr = thr; bestT = k; }
         }
+        if (bestT < 0) return fail(ctx, PMVS_E_UNSUPPORTED, "refine kernel does not fit on an SM with this configuration");
+        int pick = bestT;
+        if ((long)n < 2L * ctx->smCount * all[bestT].perSm) {          /* cannot fill the GPU twice: finish sooner instead */
+            long bestScore = 1L << 60;
+            for (int k = 0; k < 6; ++k) {
+                if (all[k].perSm < 1) continue;
+                const long cap = (long)ctx->smCount * all[k].perSm;
+                const long score = ((n + cap - 1) / cap) * ((P + cand[k] - 1) / cand[k]);
+                if (score < bestScore || (score == bestScore && k == bestT)) { bestScore = score; pick = k; }
+            }
+        }
+        cfg = all[pick];
         NW = cfg.NW;
     }
     const SmemPlan &pl = cfg.pl;

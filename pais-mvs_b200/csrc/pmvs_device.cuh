@@ -36,12 +36,17 @@
 #define PMVS_DIST_GLOBAL 1      /* distance weights read through L1 from one global table instead of a copy per CTA */
 #endif
 /* non-reference views with per-lane slots in the column loop (V = 2..16) */
-#define PMVS_COLV_VIEWS(vcap) ((vcap) < 2 ? 1 : ((vcap) > 16 ? 15 : (vcap) - 1))
+#ifndef PMVS_SLOT_VIEWS
+#define PMVS_SLOT_VIEWS 10       /* up to this many non-reference views keep per-lane slots; more form the x-part inline (L1 over slots) */
+#endif
+#define PMVS_COLV_VIEWS(vcap) ((vcap) < 2 ? 1 : ((vcap) - 1 > PMVS_SLOT_VIEWS ? PMVS_SLOT_VIEWS : (vcap) - 1))
 #define PMVS_COLV_SLOTS(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
-#define PMVS_GV_DOUBLES 6                    /* per non-reference view: h1, h4, h7, quad pointer, cols, spare */
+/* compact table of the non-reference views. Slot mode (<= PMVS_SLOT_VIEWS of them): 6 doubles each — h1, h4, h7, quad
+ * pointer, cols, spare; inline mode: 12 — h0..h8, quad pointer, cols, spare */
+#define PMVS_GV_DOUBLES_TOTAL(vcap) ((vcap) - 1 <= PMVS_SLOT_VIEWS ? 6 * ((vcap) < 2 ? 1 : (vcap) - 1) : 12 * ((vcap) - 1))
 #define PMVS_PS_PAD(ps) (((ps) + 1) & ~1)
 /* per-warp area of the column loop: per-lane slots | compact non-reference view table | per-row {fy} | per-row {py*cols, sel} */
-#define PMVS_COLV_DOUBLES(vcap, ps) (PMVS_COLV_SLOTS(vcap) + PMVS_GV_DOUBLES * PMVS_COLV_VIEWS(vcap) + 2 * PMVS_PS_PAD(ps))
+#define PMVS_COLV_DOUBLES(vcap, ps) (PMVS_COLV_SLOTS(vcap) + PMVS_GV_DOUBLES_TOTAL(vcap) + 2 * PMVS_PS_PAD(ps))
 /* homographies kept per warp: one hypothesis of vcap views, or a batch of up to 4 hypotheses with batch * V <= 32 */
 #define PMVS_HCAP(vcap) ((PMVS_EVAL_BATCH < 2 || (vcap) > 32) ? (vcap) : (PMVS_EVAL_BATCH * (vcap) < 32 ? PMVS_EVAL_BATCH * (vcap) : 32))
 #define PMVS_HYP_DOUBLES 12
@@ -88,7 +93,7 @@ struct WarpWork {
     double *ys;     /* patchSize */
     double *hyp;    /* PMVS_EVAL_BATCH HypoS records: per-hypothesis results of the batched scalar part */
     double *colv;   /* PMVS_COLV_SLOTS(vcap): per-lane column constants of the unchecked loop */
-    double *gv;     /* PMVS_GV_DOUBLES * PMVS_COLV_VIEWS(vcap): compact table of the non-reference views */
+    double *gv;     /* PMVS_GV_DOUBLES_TOTAL(vcap): compact table of the non-reference views */
     double *rowf;   /* PMVS_PS_PAD(ps): fractional part of each window row in the reference view */
     int2 *rowi;     /* PMVS_PS_PAD(ps): {floor(y) * refCols, 2 * (cvRound(y) - floor(y))} per window row */
 };
@@ -495,6 +500,19 @@ __device__ __forceinline__ double exp_table(double x, unsigned tabA) {
     return __hiloint2double(__double2hiint(p) + ((k >> 6) << 20), __double2loint(p));
 }
 
+/* compact table of the non-reference views (skipping the reference view's index): homography, quad pointer, cols */
+__device__ __forceinline__ void fill_view_table(const EvalCtx &E, const WarpWork &W, int NG, int refV) {
+    for (int k = threadIdx.x & 31; k < NG; k += 32) {
+        const int v = k + (k >= refV ? 1 : 0);
+        const ViewS &vw = E.view[v];
+        double *g = W.gv + 12 * k;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) g[q] = W.H[9 * v + q];
+        *(const uint32_t **)(g + 9) = vw.quad;
+        *(int *)(g + 10) = vw.cols;
+    }
+}
+
 template <int N>
 struct ColumnTaps {
     double ix[N], fy[N];
@@ -586,14 +604,19 @@ __device__ __forceinline__ double sum_abs_dev(const double *c, double invV) {
     return tree_sum<V>(d);
 }
 
-template <int NG, int K0>
-__device__ __forceinline__ void row_chunks(unsigned gvA, unsigned cvA, double y, double *c) {
+template <int N>
+__device__ __forceinline__ void direct_coords(unsigned gvK, double x, double y, ColumnTaps<N> &t);
+
+/* the non-reference views of one row in chunks; SLOTS: x-parts from the per-lane slots, else formed inline */
+template <int NG, int K0, bool SLOTS>
+__device__ __forceinline__ void row_chunks(unsigned gvA, unsigned cvA, double x, double y, double *c) {
     if constexpr (K0 < NG) {
         constexpr int N = (NG - K0) < PMVS_CHUNK ? (NG - K0) : PMVS_CHUNK;
         ColumnTaps<N> t;
-        column_coords<N>(gvA, cvA, K0, y, t);
+        if constexpr (SLOTS) column_coords<N>(gvA, cvA, K0, y, t);
+        else direct_coords<N>(gvA + 96u * K0, x, y, t);
         column_blend<N>(t, c + K0);
-        row_chunks<NG, K0 + N>(gvA, cvA, y, c);
+        row_chunks<NG, K0 + N, SLOTS>(gvA, cvA, x, y, c);
     }
 }
 
@@ -605,9 +628,10 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
                                              const double *__restrict__ sExpT, const WarpWork &W, int nx, int ny, double &fitOut,
                                              double &swOut) {
     constexpr int NG = V - 1;                       /* non-reference views */
+    constexpr bool SLOTS = NG <= PMVS_SLOT_VIEWS;
     const int lane = threadIdx.x & 31;
     const int G = nx <= 16 ? 32 / nx : 1;          /* row groups sharing the warp (narrow windows) */
-    const unsigned hA = smem_addr(W.H), ysA = smem_addr(W.ys), xsA = smem_addr(W.xs), distA = smem_addr(sDistW);
+    const unsigned hA = smem_addr(W.H), ysA = smem_addr(W.ys), xsA = smem_addr(W.xs), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
     const unsigned gvA = smem_addr(W.gv), rfA = smem_addr(W.rowf), riA = smem_addr(W.rowi), tabA = smem_addr(sExpT);
     const unsigned cvA = smem_addr(W.colv) + 8u * lane;
     const double invV = 1.0 / (double)V;
@@ -621,15 +645,19 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
     const int refCols = E.refCols, refV = E.refView;
 
     /* per-evaluation tables: compact non-reference view list, per-row constants of the reference view */
-    if (lane < NG) {
-        const int v = lane + (lane >= refV ? 1 : 0);
-        const ViewS &vw = E.view[v];
-        double *g = W.gv + PMVS_GV_DOUBLES * lane;
-        g[0] = W.H[9 * v + 1];
-        g[1] = W.H[9 * v + 4];
-        g[2] = W.H[9 * v + 7];
-        *(const uint32_t **)(g + 3) = vw.quad;
-        *(int *)(g + 4) = vw.cols;
+    if constexpr (SLOTS) {
+        if (lane < NG) {
+            const int v = lane + (lane >= refV ? 1 : 0);
+            const ViewS &vw = E.view[v];
+            double *g = W.gv + 6 * lane;
+            g[0] = W.H[9 * v + 1];
+            g[1] = W.H[9 * v + 4];
+            g[2] = W.H[9 * v + 7];
+            *(const uint32_t **)(g + 3) = vw.quad;
+            *(int *)(g + 4) = vw.cols;
+        }
+    } else {
+        fill_view_table(E, W, NG, refV);
     }
     for (int j = lane; j < ny; j += 32) {
         const double y = W.ys[j];
@@ -647,7 +675,7 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
         const bool active = G > 1 ? g < G : lane < span;
         const double x = lds_f64(xsA + 8u * (active ? i : i0));
 #pragma unroll
-        for (int k = 0; k < NG; ++k) {
+        for (int k = 0; k < (SLOTS ? NG : 0); ++k) {
             const unsigned h = hA + 72u * (unsigned)(k + (k >= refV ? 1 : 0));
             sts_f64_v(cvA + 256u * (3 * k), fma(lds_f64(h), x, lds_f64(h + 16u)));
             sts_f64_v(cvA + 256u * (3 * k + 1), fma(lds_f64(h + 24u), x, lds_f64(h + 40u)));
@@ -688,7 +716,7 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
                     double c[V];
                     bool kp;
                     c[NG] = ref_sample(rc, rrow ? ri1 : ri0, lds_f64(rfA + 8u * (rrow ? j2 : j)), kp);
-                    row_chunks<NG, 0>(gvA, cvA, rrow ? y1 : y0, c);
+                    row_chunks<NG, 0, SLOTS>(gvA, cvA, x, rrow ? y1 : y0, c);
                     const double sv = sum_abs_dev<V>(c, invV);
                     if (rrow) { s1 = sv; keep1 = kp; }
                     else { s0 = sv; keep0 = kp; }
@@ -732,16 +760,10 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
  * tens of chunks long).
  */
 template <int N>
-__device__ __forceinline__ void direct_coords(unsigned hA, unsigned viewA, int k0, int refV, double x, double y, ColumnTaps<N> &t) {
+__device__ __forceinline__ void direct_coords(unsigned gvK, double x, double y, ColumnTaps<N> &t) {   /* gvK: table entry of the first view */
     double w[N], r[N], e[N];
-    unsigned h[N], va[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const int v = k0 + k + (k0 + k >= refV ? 1 : 0);
-        h[k] = hA + 72u * (unsigned)v;
-        va[k] = viewA + (unsigned)sizeof(ViewS) * (unsigned)v;
-        w[k] = fma(lds_f64(h[k] + 56u), y, fma(lds_f64(h[k] + 48u), x, lds_f64(h[k] + 64u)));
-    }
+    for (int k = 0; k < N; ++k) w[k] = fma(lds_f64(gvK + 96u * k + 56u), y, fma(lds_f64(gvK + 96u * k + 48u), x, lds_f64(gvK + 96u * k + 64u)));
 #pragma unroll
     for (int k = 0; k < N; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[k]) : "d"(w[k]));
 #pragma unroll
@@ -752,8 +774,8 @@ __device__ __forceinline__ void direct_coords(unsigned hA, unsigned viewA, int k
     for (int k = 0; k < N; ++k) r[k] = fma(r[k], e[k], r[k]);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        t.ix[k] = fma(lds_f64(h[k] + 8u), y, fma(lds_f64(h[k]), x, lds_f64(h[k] + 16u))) * r[k];
-        t.fy[k] = fma(lds_f64(h[k] + 32u), y, fma(lds_f64(h[k] + 24u), x, lds_f64(h[k] + 40u))) * r[k];     /* iy */
+        t.ix[k] = fma(lds_f64(gvK + 96u * k + 8u), y, fma(lds_f64(gvK + 96u * k), x, lds_f64(gvK + 96u * k + 16u))) * r[k];
+        t.fy[k] = fma(lds_f64(gvK + 96u * k + 32u), y, fma(lds_f64(gvK + 96u * k + 24u), x, lds_f64(gvK + 96u * k + 40u))) * r[k];     /* iy */
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -762,8 +784,8 @@ __device__ __forceinline__ void direct_coords(unsigned hA, unsigned viewA, int k
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(va[k] + (unsigned)offsetof(ViewS, quad));
-        const int cols = lds_s32(va[k] + (unsigned)offsetof(ViewS, cols));
+        const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(gvK + 96u * k + 72u);
+        const int cols = lds_s32(gvK + 96u * k + 80u);
         t.px[k] = __double2loint(w[k]);
         t.q[k] = __ldg(quad + (__double2loint(r[k]) * cols + t.px[k]));
     }
@@ -773,12 +795,11 @@ __device__ __forceinline__ void direct_coords(unsigned hA, unsigned viewA, int k
 
 /* PASS 0: sum of the colours of views [k0, k0+N) of both rows; PASS 1: sum of |colour - mean| */
 template <int N, int PASS>
-__device__ __forceinline__ void many_chunk(unsigned hA, unsigned viewA, int k0, int refV, double x, double y0, double y1, double m0,
-                                           double m1, double &a0, double &a1) {
+__device__ __forceinline__ void many_chunk(unsigned gvK, double x, double y0, double y1, double m0, double m1, double &a0, double &a1) {
     ColumnTaps<N> ta, tb;
     double ca[N], cb[N];
-    direct_coords<N>(hA, viewA, k0, refV, x, y0, ta);
-    direct_coords<N>(hA, viewA, k0, refV, x, y1, tb);
+    direct_coords<N>(gvK, x, y0, ta);
+    direct_coords<N>(gvK, x, y1, tb);
     column_blend<N>(ta, ca);
     column_blend<N>(tb, cb);
     if (PASS == 1) {
@@ -795,12 +816,13 @@ __device__ __noinline__ void fitness_columns_many(const DevScene &S, const EvalC
     const int V = E.V, NG = V - 1, refV = E.refView;
     const int lane = threadIdx.x & 31;
     const int G = nx <= 16 ? 32 / nx : 1;
-    const unsigned hA = smem_addr(W.H), ysA = smem_addr(W.ys), xsA = smem_addr(W.xs), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
+    const unsigned ysA = smem_addr(W.ys), xsA = smem_addr(W.xs), distA = smem_addr(sDistW), gvA = smem_addr(W.gv);
     const unsigned rfA = smem_addr(W.rowf), riA = smem_addr(W.rowi), tabA = smem_addr(sExpT);
     const double invV = 1.0 / (double)V;
     const double negK = S.cfg.adaptiveDifferenceEnable ? -(invV * invV) / S.cfg.diffWeighting : 0.0;
     const bool expSafe = -(255.0 * 255.0) / S.cfg.diffWeighting >= -700.0;
     const int refCols = E.refCols;
+    fill_view_table(E, W, NG, refV);
     for (int j = lane; j < ny; j += 32) {
         const double y = W.ys[j];
         const double ty = __dadd_rd(y, PMVS_MAGIC_FLOOR);
@@ -833,16 +855,16 @@ __device__ __noinline__ void fitness_columns_many(const DevScene &S, const EvalC
             double s0 = cr0, s1 = cr1;
             int k0 = 0;
 #pragma unroll 1
-            for (; k0 + 4 <= NG; k0 += 4) many_chunk<4, 0>(hA, viewA, k0, refV, x, y0, y1, 0.0, 0.0, s0, s1);
+            for (; k0 + 4 <= NG; k0 += 4) many_chunk<4, 0>(gvA + 96u * k0, x, y0, y1, 0.0, 0.0, s0, s1);
 #pragma unroll 1
-            for (; k0 < NG; ++k0) many_chunk<1, 0>(hA, viewA, k0, refV, x, y0, y1, 0.0, 0.0, s0, s1);
+            for (; k0 < NG; ++k0) many_chunk<1, 0>(gvA + 96u * k0, x, y0, y1, 0.0, 0.0, s0, s1);
             const double m0 = s0 * invV, m1 = s1 * invV;
             s0 = fabs(cr0 - m0);
             s1 = fabs(cr1 - m1);
 #pragma unroll 1
-            for (k0 = 0; k0 + 4 <= NG; k0 += 4) many_chunk<4, 1>(hA, viewA, k0, refV, x, y0, y1, m0, m1, s0, s1);
+            for (k0 = 0; k0 + 4 <= NG; k0 += 4) many_chunk<4, 1>(gvA + 96u * k0, x, y0, y1, m0, m1, s0, s1);
 #pragma unroll 1
-            for (; k0 < NG; ++k0) many_chunk<1, 1>(hA, viewA, k0, refV, x, y0, y1, m0, m1, s0, s1);
+            for (; k0 < NG; ++k0) many_chunk<1, 1>(gvA + 96u * k0, x, y0, y1, m0, m1, s0, s1);
             keep1 = keep1 && two;
             double w0 = 1.0, w1 = 1.0;
             if (S.cfg.adaptiveDistanceEnable) {                                               /* patch.cpp:1030-1032 */
