@@ -393,7 +393,7 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     s.distW = ctx->dDistW;
     s.nCams = ctx->nCams;
     s.seed = ctx->seed;
-    s.tune = getenv("PMVS_TUNE") ? atoi(getenv("PMVS_TUNE")) : 1;
+    s._pad = 0;
     for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
     /* correlation scratch: one slab per resident CTA */
     const size_t stride = (size_t)ctx->vcap * ctx->cfg.patchSize * ctx->cfg.patchSize;

@@ -67,7 +67,7 @@ struct DevScene {
     const double *distW;       /* patchSize^2, index x*patchSize+y (mvs.cpp:104-109) */
     double *scratch;           /* per-CTA correlation windows: scratchStride doubles per CTA */
     unsigned long long scratchStride;
-    int nCams, tune;           /* tune: experiment switches (bit 0: column constants in shared memory) */
+    int nCams, _pad;
     uint64_t seed;
     double lodScale[PMVS_MAX_LEVELS];
 };
@@ -413,7 +413,8 @@ __device__ __forceinline__ double quad_bilinear_fast(const uint32_t *__restrict_
 }
 
 /*
- * Unchecked sample loop for exactly V views (compile-time, 2..16), one of which is the reference view.
+ * Unchecked sample loop for exactly V views (compile-time, 2..16; more views: fitness_columns_many below), one of which is
+ * the reference view.
  *
  * Lane = one window column (several row groups when the window is narrow, several column passes when it is wider
  * than 32), so the x-dependent part of every homography row, A = H0*x+H2, B = H3*x+H5, C = H6*x+H8, is computed once
@@ -433,6 +434,9 @@ __device__ __forceinline__ double quad_bilinear_fast(const uint32_t *__restrict_
  * The reference view has H = I (patch.cpp:317-319): its sample is (x, y) bit for bit, so its pixel index and
  * fractions are per-column / per-row constants (no homography, reciprocal or floor), and the background-mask pixel
  * img(cvRound(y), cvRound(x)) (patch.cpp:986) is one of the four bytes of the tap word it loads anyway.
+ * Above PMVS_SLOT_VIEWS non-reference views the slots would take so much shared memory (768 B per view and warp) that
+ * occupancy and the L1 the taps live in suffer: those instantiations form the x-part inline from a compact homography
+ * table, X = fma(h1, y, fma(h0, x, h2)) — the same expression, three more fma per sample.
  * The body is branch-free; each lane sums its rows in ascending order, then the fixed xor-tree.
  */
 __device__ __forceinline__ double lds_f64_v(unsigned a) {   /* ordered against the volatile stores below */
