@@ -913,6 +913,7 @@ int pmvs_pso_test(pmvs_ctx *ctx, int n, const double *L, const double *U, const 
     CK(cudaMalloc(&dp, sizeof(PsoTestProblem) * n));
     cudaError_t e = cudaMalloc(&dr, sizeof(PsoTestResult) * n);
     if (e != cudaSuccess) { cudaFree(dp); return fail(ctx, PMVS_E_NOMEM, "cudaMalloc failed"); }
+    cudaMemsetAsync(dr, 0, sizeof(PsoTestResult) * n, ctx->stream);      /* particle slots beyond P are copied back too */
     std::vector<PsoTestResult> hr(n);
     e = cudaMemcpy(dp, pr.data(), sizeof(PsoTestProblem) * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {

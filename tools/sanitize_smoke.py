@@ -26,5 +26,22 @@ with PatchRefiner(cfg, lean) as pr:
     seeds = sc.patches(3, seed=2, ptype=abi.TYPE_SEED)
     out2 = pr.refine(seeds)
     r = pr.pso_test([dict(L=[-1, -1, 0], U=[1, 1, 2], init=None, maxIter=5, P=9, fn=0, key=7)])
+# the flag-free fast loop (distance + difference weights only), the batched scalar part and the latency launch configurations
+cfg2 = abi.readme_config()
+cfg2.patchRadius, cfg2.patchSize, cfg2.distWeighting, cfg2.maxLOD = 4, 9, 4 / 3.0, 1
+cfg2.particleNum, cfg2.maxIteration = 7, 3
+sc2 = scene.SynthScene(cfg2, nviews=5, width=160, height=120, seed=6, tex_size=256)
+with PatchRefiner(cfg2, sc2.records) as pr:
+    out3 = pr.refine(sc2.patches(5, seed=3), flags=abi.F_POST_REMOVE_INVISIBLE)
+    f3 = pr.fitness(scene.hypotheses_from_patches(sc2, sc2.patches(4, seed=4), cfg2, per_patch=2))
+# more than 16 views: the two-pass many-view loop; 12 views: inline x-parts instead of per-lane slots
+for nv in (18, 12):
+    sc3 = scene.SynthScene(cfg2, nviews=nv, width=160, height=120, seed=7, tex_size=256, arc_deg=30.0)
+    with PatchRefiner(cfg2, sc3.records) as pr:
+        f4 = pr.fitness(scene.hypotheses_from_patches(sc3, sc3.patches(3, seed=5), cfg2, per_patch=2))
+        out4 = pr.refine(sc3.patches(2, seed=6))
+# the -f pair scan
+cnt = api.neighbor_counts(np.random.RandomState(0).rand(700, 3), 0.1)
 pyr = api.build_pyramid(sc.cams[0].levels[0][0], cfg.lodRatio, 2, with_edge=True)
-print("sanitize workload ok", len(f), sum(1 for q in out if not q.drop), sum(1 for q in out2 if not q.drop), r[0]["iterations"], len(pyr))
+print("sanitize workload ok", len(f), sum(1 for q in out if not q.drop), sum(1 for q in out2 if not q.drop), r[0]["iterations"], len(pyr),
+      sum(1 for q in out3 if not q.drop), len(f3), len(f4), sum(1 for q in out4 if not q.drop), int(cnt.sum()))
