@@ -64,7 +64,7 @@ static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t he
     pl.perWarp = (((size_t)PMVS_HCAP(vcap) * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_HYP_DOUBLES + PMVS_COLV_DOUBLES(vcap, ps);
     off += sizeof(double) * pl.perWarp * nWarps;
     pl.corrOff = off;
-    if (withCorr) off += sizeof(double) * (size_t)vcap * vcap;
+    if (withCorr && !PMVS_CORR_GLOBAL(vcap)) off += sizeof(double) * (size_t)vcap * vcap;
     pl.total = off;
     return pl;
 }
@@ -92,6 +92,8 @@ __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArg
     W.ys = W.xs + a.ps;
     W.colv = base + a.perWarp - PMVS_COLV_DOUBLES(a.vcap, a.ps);
     W.hyp = W.colv - PMVS_HYP_DOUBLES;
+    W.slotViews = PMVS_COLV_VIEWS(a.vcap);
+    W._padw = 0;
     W.gv = W.colv + PMVS_COLV_SLOTS(a.vcap);
     W.rowf = W.gv + PMVS_GV_DOUBLES_TOTAL(a.vcap);
     W.rowi = (int2 *)(W.rowf + PMVS_PS_PAD(a.ps));
@@ -198,7 +200,8 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5;
     CtaS &c = *(CtaS *)(smem + a.ctaOff);
     double *sDistW = (double *)(smem + a.distOff);
-    double *corr = (double *)(smem + a.corrOff);
+    double *hp = S.scratch + (size_t)S.scratchStride * blockIdx.x;
+    double *corr = PMVS_CORR_GLOBAL(a.vcap) ? hp + (size_t)a.vcap * a.ps * a.ps : (double *)(smem + a.corrOff);
     for (int k = tid; k < a.ps * a.ps && !PMVS_DIST_GLOBAL; k += blockDim.x) sDistW[k] = S.distW[k];
     load_exp_table(sDistW, a.ps, tid, blockDim.x);
     if (tid == 0) {
@@ -207,7 +210,6 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
     }
     const WarpWork W = warp_work(smem, a, warp);
     const WarpWork W0 = warp_work(smem, a, 0);
-    double *hp = S.scratch + (size_t)S.scratchStride * blockIdx.x;
     __syncthreads();
     for (;;) {
         if (tid == 0) c.nextIdx = atomicAdd(counter, 1);
@@ -396,7 +398,7 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     s._pad = 0;
     for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
     /* correlation scratch: one slab per resident CTA */
-    const size_t stride = (size_t)ctx->vcap * ctx->cfg.patchSize * ctx->cfg.patchSize;
+    const size_t stride = (size_t)ctx->vcap * ctx->cfg.patchSize * ctx->cfg.patchSize + (size_t)ctx->vcap * ctx->vcap + ctx->vcap;   /* windows + (global) correlation table + ratios */
     const int ctas = ctx->smCount * 4;
     if (stride > ctx->scratchStride || ctas > ctx->scratchCtas || !ctx->dScratch) {
         if (ctx->dScratch) cudaFree(ctx->dScratch);

@@ -39,7 +39,10 @@
 #ifndef PMVS_SLOT_VIEWS
 #define PMVS_SLOT_VIEWS 10       /* up to this many non-reference views keep per-lane slots; more form the x-part inline (L1 over slots) */
 #endif
-#define PMVS_COLV_VIEWS(vcap) ((vcap) < 2 ? 1 : ((vcap) - 1 > PMVS_SLOT_VIEWS ? PMVS_SLOT_VIEWS : (vcap) - 1))
+/* scenes with more than 16 cameras keep no slots at all (their shared memory goes to occupancy: the tables that scale
+ * with the camera count are large already); patches with few views take the two-pass loop there */
+#define PMVS_COLV_VIEWS(vcap) ((vcap) > 16 ? 0 : ((vcap) < 2 ? 1 : ((vcap) - 1 > PMVS_SLOT_VIEWS ? PMVS_SLOT_VIEWS : (vcap) - 1)))
+#define PMVS_CORR_GLOBAL(vcap) ((vcap) > 16)   /* the V x V correlation table (+ V region ratios) in the CTA's global scratch */
 #define PMVS_COLV_SLOTS(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
 /* compact table of the non-reference views. Slot mode (<= PMVS_SLOT_VIEWS of them): 6 doubles each — h1, h4, h7, quad
  * pointer, cols, spare; inline mode: 12 — h0..h8, quad pointer, cols, spare */
@@ -93,6 +96,7 @@ struct WarpWork {
     double *ys;     /* patchSize */
     double *hyp;    /* PMVS_EVAL_BATCH HypoS records: per-hypothesis results of the batched scalar part */
     double *colv;   /* PMVS_COLV_SLOTS(vcap): per-lane column constants of the unchecked loop */
+    int slotViews, _padw;   /* non-reference views the slot area holds */
     double *gv;     /* PMVS_GV_DOUBLES_TOTAL(vcap): compact table of the non-reference views */
     double *rowf;   /* PMVS_PS_PAD(ps): fractional part of each window row in the reference view */
     int2 *rowi;     /* PMVS_PS_PAD(ps): {floor(y) * refCols, 2 * (cvRound(y) - floor(y))} per window row */
@@ -903,6 +907,7 @@ __device__ __forceinline__ bool fitness_columns_dispatch(int nV, const DevScene 
                                                          double &sw) {
     if constexpr (V >= 2) {
         if (nV == V) {
+            if (V - 1 <= PMVS_SLOT_VIEWS && V - 1 > W.slotViews) return false;      /* no slot area in this scene: caller falls back */
             /* |deviation| <= 255 per view bounds the exponent of the difference weight */
             const double xmin = -(255.0 * 255.0) / S.cfg.diffWeighting;
             if (!S.cfg.adaptiveGradientEnable && S.cfg.adaptiveDistanceEnable && (!S.cfg.adaptiveDifferenceEnable || xmin >= -700.0))
@@ -954,7 +959,8 @@ __device__ __noinline__ double warp_window(const DevScene &S, const EvalCtx &E, 
         /* lane-per-column loop: every V in 2..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
         if (VCAP == 8 && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
         else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
-        else if (VCAP == 0 && nx > 0 && E.refView >= 0) fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
+        else if (nx > 0 && E.refView >= 0 && E.V >= 2 && (VCAP == 0 || E.V - 1 > W.slotViews))
+            fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     __syncwarp();
