@@ -170,6 +170,31 @@ def test_fitness_vs_oracle(nviews, radius, weights):
     print("V=%d r=%d: %d evaluations (%d sentinels), worst relative deviation %.3g" % (nviews, radius, n, n_max, worst))
 
 
+@pytest.mark.parametrize("subset", [3, 7, 11, 14, 17])
+def test_fitness_view_subsets_in_many_camera_scene(subset):
+    """Scenes with more than 16 cameras keep no per-lane slots (their shared memory goes to occupancy): patches that
+    see only a few of the cameras take the two-pass loop there (<= 11 views), the inline single-pass loop (12..16) or
+    the many-view loop (> 16). Also refine() on such patches."""
+    cfg = abi.readme_config()
+    cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = 6, 13, 2.0, 1
+    cfg.particleNum, cfg.maxIteration = 6, 5
+    sc = scene.SynthScene(cfg, nviews=20, width=400, height=300, seed=31, tex_size=1024, arc_deg=30.0, background=6)
+    patches = sc.patches(24, seed=3, extent=2.2)
+    rng = np.random.RandomState(subset)
+    for p in patches:                                  # keep `subset` of the 20 cameras, in ascending order like the reference
+        keep = sorted(rng.choice(20, size=subset, replace=False).tolist())
+        p.nCam = subset
+        for i, c in enumerate(keep):
+            p.camIdx[i] = c
+    hy = scene.hypotheses_from_patches(sc, patches, cfg, per_patch=3, spread=2.0)
+    o = orc.Oracle(cfg, sc.records, seed=42, use_ref_pso=orc.ref_lib() is not None)
+    with PatchRefiner(cfg, sc.records, seed=42) as pr:
+        worst = assert_fitness_close(pr.fitness(hy), o.fitness_batch(hy, threads=8))
+        got = pr.refine(patches, flags=abi.F_POST_REMOVE_INVISIBLE)
+    worst = max(worst, compare_refine(got, o.refine_batch(patches, flags=abi.F_POST_REMOVE_INVISIBLE, patch_threads=8)))
+    print("20 cameras, %d visible: worst relative deviation %.3g" % (subset, worst))
+
+
 def test_fitness_empty_and_ragged(small_scene):
     cfg, sc = small_scene
     with PatchRefiner(cfg, sc.records) as pr:
