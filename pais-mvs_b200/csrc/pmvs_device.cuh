@@ -40,7 +40,7 @@
 #define PMVS_SLOT_VIEWS 10       /* up to this many non-reference views keep per-lane slots; more form the x-part inline (L1 over slots) */
 #endif
 /* scenes with more than 16 cameras keep no slots at all (their shared memory goes to occupancy: the tables that scale
- * with the camera count are large already); patches with few views take the two-pass loop there */
+ * with the camera count are large already); every view count forms the x-parts inline there */
 #define PMVS_COLV_VIEWS(vcap) ((vcap) > 16 ? 0 : ((vcap) < 2 ? 1 : ((vcap) - 1 > PMVS_SLOT_VIEWS ? PMVS_SLOT_VIEWS : (vcap) - 1)))
 #define PMVS_CORR_GLOBAL(vcap) ((vcap) > 16)   /* the V x V correlation table (+ V region ratios) in the CTA's global scratch */
 #define PMVS_COLV_SLOTS(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
@@ -631,12 +631,12 @@ __device__ __forceinline__ void row_chunks(unsigned gvA, unsigned cvA, double x,
 /* FAST: no gradient weight and the difference weight's exponent provably in [-700, 0] — the distance weight is
  * always read (the table holds ones when it is disabled) and the difference weight always evaluated (negK = 0 when it
  * is disabled), so the row loop carries no configuration flags. */
-template <int V, bool FAST>
+template <int V, bool FAST, bool SLOTS>
 __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E, const double *__restrict__ sDistW,
                                              const double *__restrict__ sExpT, const WarpWork &W, int nx, int ny, double &fitOut,
                                              double &swOut) {
     constexpr int NG = V - 1;                       /* non-reference views */
-    constexpr bool SLOTS = NG <= PMVS_SLOT_VIEWS;
+    static_assert(!SLOTS || NG <= PMVS_SLOT_VIEWS, "slot mode holds at most PMVS_SLOT_VIEWS non-reference views");
     const int lane = threadIdx.x & 31;
     const int G = nx <= 16 ? 32 / nx : 1;          /* row groups sharing the warp (narrow windows) */
     const unsigned hA = smem_addr(W.H), ysA = smem_addr(W.ys), xsA = smem_addr(W.xs), distA = smem_addr(sDistW), viewA = smem_addr(E.view);
@@ -707,8 +707,13 @@ __device__ __noinline__ void fitness_columns(const DevScene &S, const EvalCtx &E
                 /* both rows' tap loads are in flight before the first one is consumed */
                 ColumnTaps<NG> ta, tb;
                 double ca[V], cb[V];
-                column_coords<NG>(gvA, cvA, 0, y0, ta);
-                column_coords<NG>(gvA, cvA, 0, y1, tb);
+                if constexpr (SLOTS) {
+                    column_coords<NG>(gvA, cvA, 0, y0, ta);
+                    column_coords<NG>(gvA, cvA, 0, y1, tb);
+                } else {
+                    direct_coords<NG>(gvA, x, y0, ta);
+                    direct_coords<NG>(gvA, x, y1, tb);
+                }
                 ca[NG] = ref_sample(rc, ri0, lds_f64(rfA + 8u * j), keep0);
                 cb[NG] = ref_sample(rc, ri1, lds_f64(rfA + 8u * j2), keep1);
                 column_blend<NG>(ta, ca);
@@ -907,13 +912,19 @@ __device__ __forceinline__ bool fitness_columns_dispatch(int nV, const DevScene 
                                                          double &sw) {
     if constexpr (V >= 2) {
         if (nV == V) {
-            if (V - 1 <= PMVS_SLOT_VIEWS && V - 1 > W.slotViews) return false;      /* no slot area in this scene: caller falls back */
             /* |deviation| <= 255 per view bounds the exponent of the difference weight */
             const double xmin = -(255.0 * 255.0) / S.cfg.diffWeighting;
-            if (!S.cfg.adaptiveGradientEnable && S.cfg.adaptiveDistanceEnable && (!S.cfg.adaptiveDifferenceEnable || xmin >= -700.0))
-                fitness_columns<V, true>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
-            else
-                fitness_columns<V, false>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
+            const bool fast = !S.cfg.adaptiveGradientEnable && S.cfg.adaptiveDistanceEnable && (!S.cfg.adaptiveDifferenceEnable || xmin >= -700.0);
+            /* per-lane slots when the scene keeps a slot area that holds this patch's views, else x-parts inline */
+            if constexpr (V - 1 <= PMVS_SLOT_VIEWS) {
+                if (V - 1 <= W.slotViews) {
+                    if (fast) fitness_columns<V, true, true>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
+                    else fitness_columns<V, false, true>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
+                    return true;
+                }
+            }
+            if (fast) fitness_columns<V, true, false>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
+            else fitness_columns<V, false, false>(S, E, sDistW, sExpT, W, nx, ny, fit, sw);
             return true;
         }
         return fitness_columns_dispatch<V - 1>(nV, S, E, sDistW, sExpT, W, nx, ny, fit, sw);
@@ -959,8 +970,7 @@ __device__ __noinline__ double warp_window(const DevScene &S, const EvalCtx &E, 
         /* lane-per-column loop: every V in 2..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
         if (VCAP == 8 && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
         else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
-        else if (nx > 0 && E.refView >= 0 && E.V >= 2 && (VCAP == 0 || E.V - 1 > W.slotViews))
-            fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
+        else if (VCAP == 0 && nx > 0 && E.refView >= 0) fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     __syncwarp();
