@@ -127,22 +127,22 @@ public:
     int getPatchIdFromQueue();                                      /* mvs.cpp:636-788, indexed */
     size_t byPriorityQueueSize() const { return prioQueue.size() > fifo.size() ? prioQueue.size() : fifo.size(); }
     const std::string &lastError() const { return err; }
+    void setCellMaps();                                             /* mvs.cpp:116-133 */
+    void insertPatch(const Patch &p);                               /* mvs.cpp:579-601 */
+    void deletePatch(int id);                                       /* mvs.cpp:607-634 */
+    void setEstimatedNormal(Patch &p) const;                        /* patch.cpp:390-413 */
+    void queuePush(int id);                                         /* initPriorityQueue / insertPatch's queue.push_back */
+    void queueClear();
 
 private:
     std::set<std::pair<std::pair<double, long>, int> > prioQueue;
     std::deque<int> fifo;
     long queueSeq = 0;
-    void queuePush(int id);
-    void queueClear();
     std::vector<pmvs_ctx *> ctxs;       /* one per GPU */
     std::string err;
     bool ensureContext();
-    void setCellMaps();                                             /* mvs.cpp:116-133 */
     void ensureFilterMaps();                                        /* the `if (cellMaps.empty())` prologue of every filter */
-    void insertPatch(const Patch &p);                               /* mvs.cpp:579-601 */
-    void deletePatch(int id);                                       /* mvs.cpp:607-634 */
     bool refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::vector<std::vector<int> > *parentCams);
-    void setEstimatedNormal(Patch &p) const;                        /* patch.cpp:390-413 */
     void patchColor(Patch &p) const;                                /* patch.cpp:648-652 */
 };
 

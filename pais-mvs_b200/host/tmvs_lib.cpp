@@ -474,7 +474,10 @@ void MVS::queuePush(int id) {
     std::map<int, Patch>::const_iterator it = patches.find(id);
     const double pr = it == patches.end() ? 0.0 : it->second.priority;
     const double key = cfg.expansionStrategy == EXPANSION_WORST_FIRST ? -pr : pr;
-    if (!std::isnan(key) && pr < DBL_MAX) prioQueue.insert(std::make_pair(std::make_pair(key, queueSeq), id));   /* NaN / DBL_MAX are never selected (:682, :717) */
+    /* never selected by the strict comparisons against the initial +-DBL_MAX (:682, :717): NaN; DBL_MAX and above under
+     * best-first; -DBL_MAX and below under worst-first */
+    const bool selectable = !std::isnan(pr) && (cfg.expansionStrategy == EXPANSION_WORST_FIRST ? pr > -DBL_MAX : pr < DBL_MAX);
+    if (selectable) prioQueue.insert(std::make_pair(std::make_pair(key, queueSeq), id));
     fifo.push_back(id);
     ++queueSeq;
 }
