@@ -7,7 +7,7 @@
  * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
  * round, default 1024), --device D, --gpus N (shard every batch over N GPUs), --seed S (run seed of the counter-based PSO
  * RNG), --autosave-seconds T (spacing of auto_save.mvs checkpoints, default 5), --no-expand, -V (verbose),
- * --convert IN OUT.mvs (load + write only: needs no GPU).
+ * --convert IN OUT.{mvs,ply,psr} (load + write only: needs no GPU).
  */
 #include <chrono>
 #include <cstdio>
@@ -111,7 +111,13 @@ int main(int argc, char **argv) {
     loadConfig(configFile.c_str(), config);                  /* TMVS.cpp:92-93: config.txt wins over the MVS header */
     mvs.setConfig(config);
     printf("cameras: %zu patches: %zu\n", mvs.cameras.size(), mvs.patches.size());
-    if (mode == "--convert") return mvs.writeMVS(convertOut.c_str()) ? 0 : 1;
+    if (mode == "--convert") {   /* writer by extension: MVS_V3 (default), .ply, .psr */
+        const size_t dot = convertOut.find_last_of('.');
+        const std::string ext = dot == std::string::npos ? "" : convertOut.substr(dot + 1);
+        if (ext == "ply") return mvs.writePLY(convertOut.c_str()) ? 0 : 1;
+        if (ext == "psr") return mvs.writePSR(convertOut.c_str()) ? 0 : 1;
+        return mvs.writeMVS(convertOut.c_str()) ? 0 : 1;
+    }
     if (mode == "-f") return runFiltering(mvs, input, outDir);
     if (mvs.patches.empty()) {
         fprintf(stderr, "no seed points in the input (SIFT seed generation, featuremanager.cpp, is out of scope)\n");

@@ -1076,12 +1076,25 @@ bool MVS::loadMVS(const char *fileName) {   /* fileloader.cpp:403-472 */
                 spherical2Normal(p.normalS, p.normal);
                 p.type = PMVS_TYPE_SEED;      /* loader ctor marks TYPE_SEED, patch.cpp:45-59 */
                 p.id = nextId++;
-                for (size_t k = 0; k < p.camIdx.size(); ++k) {   /* setImagePoint, patch.cpp:627-653 */
+                /* the loader ctor (patch.cpp:45-59) goes on to setReferenceCameraIndex (:415-445: arg-max of
+                 * normal . -opticalNormal, strict >, first wins) and setImagePoint (:627-653: projections and the
+                 * colour under the reference camera's projection) — what `-f` writes into its PLY files. Depth range,
+                 * LOD and priority are recomputed by refine() before anything reads them. */
+                double maxCorr = -DBL_MAX;
+                for (size_t k = 0; k < p.camIdx.size(); ++k) {
+                    if (p.camIdx[k] < 0 || p.camIdx[k] >= (int)cameras.size()) continue;
+                    const double *on = cameras[p.camIdx[k]].opticalNormal;
+                    const double neg[3] = {-on[0], -on[1], -on[2]};
+                    const double corr = dot3(p.normal, neg);
+                    if (corr > maxCorr) { maxCorr = corr; p.refCamIdx = p.camIdx[k]; }
+                }
+                for (size_t k = 0; k < p.camIdx.size(); ++k) {
                     double pt[2] = {0, 0};
                     if (p.camIdx[k] >= 0 && p.camIdx[k] < (int)cameras.size()) cameras[p.camIdx[k]].project(p.center, pt, 0, cfg.lodRatio);
                     p.imgPoint.push_back(pt[0]);
                     p.imgPoint.push_back(pt[1]);
                 }
+                patchColor(p);
                 patches.insert(std::pair<int, Patch>(p.id, p));
             }
             stage = 3;

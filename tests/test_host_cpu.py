@@ -68,3 +68,57 @@ def test_usage_and_out_of_scope_commands(tmvs_bin):
     assert r.returncode == 2 and "scope" in r.stderr
     r = subprocess.run([tmvs_bin, "-f", "missing.mvs"], capture_output=True, text=True)  # filtering: in scope, file missing
     assert r.returncode == 1 and "load failed" in r.stderr
+
+
+def test_mvs_v2_ply_psr_and_loader_ctor(tmvs_bin, dataset, tmp_path):
+    """MVS_V2 input (no config block, fileloader.cpp:431-434), and the PLY / PSR writers byte for byte against the format of
+    filewriter.cpp:104-171: ostream default formatting (%g) of centre and normal, colour written r g b from the b,g,r
+    pixel under the reference camera's projection — the loader ctor's setReferenceCameraIndex + setImagePoint
+    (patch.cpp:45-59, :415-445, :627-653) — and six float32 per patch."""
+    import orc_host as oh
+    d, path, cfg, sc = dataset
+    rng = np.random.RandomState(11)
+    patches = []
+    for k in range(40):
+        center = [0.8 * (2 * rng.rand() - 1), 0.6 * (2 * rng.rand() - 1), sc.plane_z + 0.01 * rng.randn()]
+        cams = sorted(rng.choice(len(sc.cams), size=rng.randint(3, len(sc.cams) + 1), replace=False).tolist())
+        patches.append(dict(center=center, normalS=[0.35 * rng.rand(), 2 * math.pi * rng.rand() - math.pi], camIdx=cams,
+                            fitness=float(rng.rand()), correlation=float(rng.rand())))
+    v3 = os.path.join(d, "p.mvs")
+    mvsio.write_mvs(v3, cfg, sc.cams, patches)
+    # MVS_V2 = the same records without the 160-byte config block
+    raw = open(v3, "rb").read()
+    v2 = str(tmp_path / "p_v2.mvs")
+    open(v2, "wb").write(b"MVS_V2\n" + raw[7 + 160:])
+    conf = os.path.join(d, "config.txt")
+    out_v2, ply, psr = str(tmp_path / "from_v2.mvs"), str(tmp_path / "p.ply"), str(tmp_path / "p.psr")
+    for src, dst in ((v2, out_v2), (v3, ply), (v3, psr)):
+        subprocess.check_call([tmvs_bin, "--convert", src, dst, "--config", conf, "--image-dir", d], cwd=d)
+    got = open(out_v2, "rb").read()                                      # V2 in, config.txt applied, V3 out: identical records
+    assert got[:7 + 112] == raw[:7 + 112] and got[7 + 120:] == raw[7 + 120:]      # (neighborRadius, bytes 112..119, is derived at run time)
+
+    ocams = [oh.Camera(c.focal[0], list(c.quaternion), list(c.center), sc.width, sc.height, c.levels[0][0]) for c in sc.cams]
+    want_lines, want_psr = [], []
+    for p in patches:
+        th, ph = p["normalS"]
+        n = [math.sin(th) * math.cos(ph), math.sin(th) * math.sin(ph), math.cos(th)]           # utility.h:25-29
+        ref, best = -1, -oh.DBL_MAX
+        for ci in p["camIdx"]:
+            on = ocams[ci].optical_normal
+            corr = oh.dot3(n, [-on[0], -on[1], -on[2]])
+            if corr > best:
+                best, ref = corr, ci
+        colour = (0, 0, 0)
+        (u, v), inside = ocams[ref].project(p["center"], 0, cfg.lodRatio)
+        if inside:
+            g = int(ocams[ref].grey[min(oh.cv_round(v), sc.height - 1)][min(oh.cv_round(u), sc.width - 1)])
+            colour = (g, g, g)                                                                   # PGM: r = g = b
+        want_lines.append("%g %g %g %g %g %g %d %d %d" % (*p["center"], *n, *colour))
+        want_psr.append(np.array([*p["center"], *n], dtype=np.float32))
+    text = open(ply).read().split("\n")
+    assert text[:13] == ["ply", "format ascii 1.0", "element vertex 40", "property float x", "property float y", "property float z",
+                         "property float nx", "property float ny", "property float nz", "property uchar diffuse_red",
+                         "property uchar diffuse_green", "property uchar diffuse_blue", "end_header"]
+    assert text[13:53] == want_lines and text[53:] == [""]
+    assert len({l.split()[-1] for l in want_lines}) > 10                  # real image colours, not a constant
+    assert open(psr, "rb").read() == np.stack(want_psr).astype("<f4").tobytes()
