@@ -2,7 +2,7 @@
  * tmvs_hooks.cpp — plain-C test hooks over the host driver's caller-side functions (last row:
  * getExpansionPatchCenter, skipNeighborCell, runtimeFiltering, insertPatch / deletePatch, the queue pops, isNeighbor,
  * reCentering, setNeighborRadius, Camera::project, cell maps). Built as pais-mvs_b200/lib/libtmvs_host.so so that
- * tests/test_host_parity_cpu.py can drive them from ctypes against oracle/orc_host.py, a restatement of the reference
+ * tests/test_host_parity_cpu.py can drive them from ctypes against the test suite's restatement of the reference
  * lines. Nothing here is on the product path: `tmvs` does not link this file and no GPU is touched (no context is created).
  */
 #include <cstring>
