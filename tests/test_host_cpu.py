@@ -122,3 +122,22 @@ def test_mvs_v2_ply_psr_and_loader_ctor(tmvs_bin, dataset, tmp_path):
     assert text[13:53] == want_lines and text[53:] == [""]
     assert len({l.split()[-1] for l in want_lines}) > 10                  # real image colours, not a constant
     assert open(psr, "rb").read() == np.stack(want_psr).astype("<f4").tobytes()
+
+
+def test_config_txt_parser(tmvs_bin, dataset, tmp_path):
+    """config.txt as fileloader.cpp:474-565 reads it: '#' comment lines, blank lines, blanks or tabs between key and value,
+    CRLF line ends, unknown keys ignored, later lines win, patchSize follows patchRadius; plus the documented
+    gradientWeighting key (README.md:140-142) the reference parser forgot."""
+    d, path, cfg, sc = dataset
+    conf = str(tmp_path / "c.txt")
+    open(conf, "wb").write(b"# comment\r\n\r\npatchRadius\t9\r\nparticleNum 7\nparticleNum   11\n#maxIteration 99\nmaxIteration 21 trailing words\n"
+                           b"unknownKey 5\nadaptiveGradientEnable 1\ngradientWeighting 0.125\nadaptiveDistanceEnable 0\nlodRatio 0.75\n"
+                           b"expansionStrategy 2\nminRegionRatio\t0.4\nkeyWithoutValue\nneighborRadiusScalar 0.02")
+    out = str(tmp_path / "c.mvs")
+    subprocess.check_call([tmvs_bin, "--convert", path, out, "--config", conf], cwd=d)
+    c, _, _ = mvsio.read_mvs(out)
+    want = abi.default_config()                                      # compiled defaults (TMVS.cpp:26-52) under the file's keys
+    assert (c.patchRadius, c.patchSize, c.particleNum, c.maxIteration) == (9, 19, 11, 21)
+    assert (c.adaptiveGradientEnable, c.adaptiveDistanceEnable, c.adaptiveDifferenceEnable) == (1, 0, want.adaptiveDifferenceEnable)
+    assert (c.gradientWeighting, c.lodRatio, c.expansionStrategy, c.minRegionRatio, c.neighborRadiusScalar) == (0.125, 0.75, 2, 0.4, 0.02)
+    assert (c.cellSize, c.minCamNum, c.maxCellPatchNum, c.distWeighting) == (want.cellSize, want.minCamNum, want.maxCellPatchNum, want.distWeighting)
