@@ -124,17 +124,23 @@ int main(int argc, char **argv) {
         return 1;
     }
 
-    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    typedef std::chrono::steady_clock Clock;
+    const Clock::time_point t0 = Clock::now();
     mvs.writeMVS((outDir + "init.mvs").c_str());
     if (!mvs.refineSeedPatches()) { fprintf(stderr, "seed refinement failed: %s\n", mvs.lastError().c_str()); return 1; }
     printf("seeds kept: %zu\n", mvs.patches.size());
     mvs.writeMVS((outDir + "seed.mvs").c_str());
+    const Clock::time_point t1 = Clock::now();
     if (expand && !mvs.expansionPatches()) { fprintf(stderr, "expansion failed: %s\n", mvs.lastError().c_str()); return 1; }
+    const Clock::time_point t2 = Clock::now();
     mvs.writeMVS((outDir + "exp.mvs").c_str());
     mvs.writePLY((outDir + "exp.ply").c_str());
     mvs.writePSR((outDir + "exp.psr").c_str());
-    const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const Clock::time_point t3 = Clock::now();
+    const double total = std::chrono::duration<double>(t3 - t0).count();
     printf("patches: %zu refined: %ld gpu_seconds: %f\n", mvs.patches.size(), mvs.refinedCount, mvs.gpuSeconds);
+    printf("phase seconds: seeds %.3f (context %.3f) expansion %.3f output %.3f\n", std::chrono::duration<double>(t1 - t0).count(),
+           mvs.contextSeconds, std::chrono::duration<double>(t2 - t1).count(), std::chrono::duration<double>(t3 - t2).count());
     printf("time1\t%f\n", total);                            /* TMVS.cpp:118-119 */
     return 0;
 }

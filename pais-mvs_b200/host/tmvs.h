@@ -90,7 +90,8 @@ public:
     bool verbose = false;
     std::string imageDir;              /* prefix for camera image files */
     long refinedCount = 0;             /* patches sent through refine() */
-    double gpuSeconds = 0;
+    double gpuSeconds = 0;             /* inside pmvs_refine_batch calls */
+    double contextSeconds = 0;         /* pmvs_create: CUDA context, module load, pyramid upload + build */
 
     explicit MVS(const MvsConfig &c);
     ~MVS();

@@ -534,6 +534,7 @@ bool MVS::ensureContext() {
             r.level[l].edge = nullptr;
         }
     }
+    const std::chrono::steady_clock::time_point tc0 = std::chrono::steady_clock::now();
     for (int g = 0; g < (numGpus > 0 ? numGpus : 1); ++g) {
         pmvs_ctx *c = nullptr;
         const int rc = pmvs_create(&c, &cfg, (int)recs.size(), recs.data(), device + g, rngSeed);
@@ -546,6 +547,7 @@ bool MVS::ensureContext() {
         }
         ctxs.push_back(c);
     }
+    contextSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count();
     return true;
 }
 
