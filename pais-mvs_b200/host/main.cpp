@@ -6,7 +6,8 @@
  *
  * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
  * round, default 1024), --device D, --gpus N (shard every batch over N GPUs), --seed S (run seed of the counter-based PSO
- * RNG), --autosave-seconds T (spacing of auto_save.mvs checkpoints, default 5), --no-expand, -V (verbose),
+ * RNG), --merge-slots / --slot-passes (one GPU pass per round over all camera slots, or one per slot: the reference's visiting order),
+ * --autosave-seconds T (spacing of auto_save.mvs checkpoints, default 5), --no-expand, -V (verbose),
  * --convert IN OUT.{mvs,ply,psr} (load + write only: needs no GPU).
  */
 #include <chrono>
@@ -66,7 +67,7 @@ int main(int argc, char **argv) {
     int roundSize = 1024, device = 0, gpus = 1;
     unsigned long long seed = 42;
     double autosave = 5.0;
-    bool expand = true, verbose = false;
+    bool expand = true, verbose = false, mergeSlots = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if ((a == "-r" || a == "-f" || a == "-v" || a == "-a") && i + 1 < argc) { mode = a; input = argv[++i]; }
@@ -80,6 +81,8 @@ int main(int argc, char **argv) {
         else if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
         else if (a == "--autosave-seconds" && i + 1 < argc) autosave = atof(argv[++i]);
         else if (a == "--no-expand") expand = false;
+        else if (a == "--merge-slots") mergeSlots = true;
+        else if (a == "--slot-passes") mergeSlots = false;
         else if (a == "-V") verbose = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -105,6 +108,7 @@ int main(int argc, char **argv) {
     mvs.rngSeed = seed;
     mvs.autosaveSeconds = autosave;
     mvs.verbose = verbose;
+    mvs.mergeSlots = mergeSlots;
     mvs.imageDir = imageDir;
 
     if (!loadAny(mvs, input)) { fprintf(stderr, "load failed: %s\n", mvs.lastError().c_str()); return 1; }

@@ -83,6 +83,7 @@ public:
     std::vector<int> queue;            /* insertion order (the reference's container) */
     int nextId = 0;
     int roundSize = 1024;              /* parents popped per expansion round */
+    bool mergeSlots = false;           /* one GPU pass per round over all camera slots (expected-neighbour prediction) instead of one per slot */
     int device = 0;                    /* first device */
     int numGpus = 1;                   /* devices device .. device+numGpus-1, candidates sharded by index */
     uint64_t rngSeed = 42;

@@ -653,7 +653,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     typedef std::chrono::steady_clock Clock;
     double tPop = 0, tGen = 0, tCommit = 0, tSave = 0;
     Clock::time_point lastSave = Clock::now();
-    long gpuCalls = 0;
+    long gpuCalls = 0, refinedMax = 0;
     for (int round = 0;; ++round) {
         /* 1. pop up to roundSize parents in strategy order */
         Clock::time_point tp0 = Clock::now();
@@ -675,7 +675,22 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
          * A round therefore runs one pass per camera slot i: candidates of slot i for all parents -> GPU -> serial
          * commit in parent order -> slot i+1 sees the updated cell maps. */
         size_t nCands = 0, accepted = 0;
-        for (size_t slot = 0;; ++slot) {
+        size_t maxSlots = 0;
+        for (size_t k = 0; k < parents.size(); ++k) {
+            std::map<int, Patch>::const_iterator pit = patches.find(parents[k]);
+            if (pit != patches.end()) maxSlots = std::max(maxSlots, pit->second.camIdx.size());
+        }
+        /* mergeSlots: ONE pass per round over all camera slots (slot-major, the order the per-slot passes commit in).
+         * What the per-slot passes learn from the commits in between — "this cell now holds a neighbour of the parent"
+         * (skipNeighborCell, mvs.cpp:803-804) — is predicted instead: a candidate is expected to land in the cells its
+         * unrefined centre projects to in its parent's cameras, with its parent's normal. A later candidate whose
+         * target cell holds such an expected neighbour of ITS parent is not generated. Mispredictions (refinement moved
+         * the centre across a cell border, or the expected patch was rejected) cost a wasted refinement or leave a cell
+         * to a later round; the commit below still re-checks every target cell against the real state. The sparse
+         * passes of slots 1.. (tens of candidates, a full kernel latency each) disappear: 5x fewer, 5x larger calls. */
+        std::map<std::pair<int, std::pair<int, int> >, std::vector<int> > expected;   /* cell -> indices into cpatch (merged mode) */
+        for (size_t slot0 = 0; slot0 < maxSlots; slot0 = mergeSlots ? maxSlots : slot0 + 1) {
+            const size_t slot1 = mergeSlots ? maxSlots : slot0 + 1;
             Clock::time_point tg0 = Clock::now();
             std::vector<Cand> cands;
             std::vector<Patch> cpatch;
@@ -684,6 +699,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
              * candidates for a cell than it still has room for — the serial reference would have skipped them */
             std::map<std::pair<int, std::pair<int, int> >, int> pending;
             bool anySlot = false;
+            for (size_t slot = slot0; slot < slot1; ++slot)
             for (size_t k = 0; k < parents.size(); ++k) {
                 std::map<int, Patch>::const_iterator pit = patches.find(parents[k]);
                 if (pit == patches.end()) continue;
@@ -697,8 +713,16 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 for (int j = 0; j < 4; ++j) {
                     if (!m.inMap(nx[j], ny[j])) continue;
                     if (skipNeighborCell(m.cell(nx[j], ny[j]), pth)) continue;
-                    int &pend = pending[std::make_pair(ci, std::make_pair(nx[j], ny[j]))];
+                    const std::pair<int, std::pair<int, int> > cellKey = std::make_pair(ci, std::make_pair(nx[j], ny[j]));
+                    int &pend = pending[cellKey];
                     if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
+                    if (mergeSlots) {
+                        std::map<std::pair<int, std::pair<int, int> >, std::vector<int> >::const_iterator ex = expected.find(cellKey);
+                        bool taken = false;
+                        if (ex != expected.end())
+                            for (size_t q = 0; q < ex->second.size() && !taken; ++q) taken = isNeighbor(pth, cpatch[ex->second[q]], cfg.neighborRadius);
+                        if (taken) continue;
+                    }
                     ++pend;
                     Patch e;                                   /* Patch(center, parent), patch.cpp:36-43 */
                     e.type = PMVS_TYPE_EXPAND;
@@ -710,12 +734,20 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                     cands.push_back(c);
                     cpatch.push_back(e);
                     parentCams.push_back(pth.camIdx);
+                    if (mergeSlots)
+                        for (size_t v = 0; v < pth.camIdx.size(); ++v) {
+                            double pt[2];
+                            const int cv = pth.camIdx[v];
+                            if (!cameras[cv].project(e.center, pt, 0, cfg.lodRatio)) continue;
+                            expected[std::make_pair(cv, std::make_pair((int)(pt[0] / cfg.cellSize), (int)(pt[1] / cfg.cellSize)))].push_back((int)cpatch.size() - 1);
+                        }
                 }
             }
             tGen += std::chrono::duration<double>(Clock::now() - tg0).count();
             if (!anySlot) break;
             if (cands.empty()) continue;
             ++gpuCalls;
+            refinedMax = std::max(refinedMax, (long)cands.size());
             /* expandVisibleCamera + refine + removeInvisibleCamera on the GPU (mvs.cpp:572-574) */
             std::vector<Patch *> batch(cpatch.size());
             for (size_t k = 0; k < cpatch.size(); ++k) batch[k] = &cpatch[k];
@@ -746,7 +778,8 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             tSave += std::chrono::duration<double>(Clock::now() - ts0).count();
         }
     }
-    printf("expansion host seconds: pop %.3f generate %.3f commit %.3f auto_save %.3f; gpu calls %ld\n", tPop, tGen, tCommit, tSave, gpuCalls);
+    printf("expansion host seconds: pop %.3f generate %.3f commit %.3f auto_save %.3f; gpu calls %ld (largest %ld candidates)\n", tPop, tGen, tCommit,
+           tSave, gpuCalls, refinedMax);
     setNeighborRadius();
     return true;
 }

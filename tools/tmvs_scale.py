@@ -1,5 +1,5 @@
 """End-to-end timing of `tmvs -r` on a synthetic NVM scene: how much of the wall clock is GPU refinement vs the host's
-serial commit (the expected scaling limit). usage: python tools/tmvs_scale.py [width height round cell]"""
+serial commit (the expected scaling limit). usage: python tools/tmvs_scale.py [width height round cell [extra tmvs -r switches ...]]"""
 import os
 import subprocess
 import sys
@@ -23,10 +23,19 @@ with tempfile.TemporaryDirectory() as d:
     mvsio.write_config(os.path.join(d, "config.txt"), cfg)
     t0 = time.time()
     r = subprocess.run([os.path.join(ROOT, "pais-mvs_b200", "bin", "tmvs"), "-r", path, "--config", os.path.join(d, "config.txt"),
-                        "--out-dir", d, "--round", rnd], cwd=d, capture_output=True, text=True)
+                        "--out-dir", d, "--round", rnd] + sys.argv[5:], cwd=d, capture_output=True, text=True)
     dt = time.time() - t0
-    print(r.stdout[-600:], r.stderr[-400:])
+    print(r.stdout[-700:], r.stderr[-400:])
     print("wall %.2f s (incl. image load + pyramid build)" % dt)
+    # quality of the reconstruction: the scene is the plane z = plane_z seen by every camera
+    import numpy as np
+    _, _, exp = mvsio.read_mvs(os.path.join(d, "exp.mvs"))
+    z = np.array([p["center"][2] for p in exp])
+    th = np.array([p["normalS"][0] for p in exp])
+    cells = {(int(u / cell), int(v / cell)) for u, v in (sc.cams[0].project(np.array(p["center"])) for p in exp)}
+    print("quality: %d patches, |z - plane| p50 %.2e p95 %.2e, tilt p95 %.3f rad, %d cells of camera 0 covered (of %d)"
+          % (len(exp), np.percentile(np.abs(z - sc.plane_z), 50), np.percentile(np.abs(z - sc.plane_z), 95), np.percentile(th, 95),
+             len(cells), (w // cell) * (h // cell)))
     # the -f post-process on the reconstruction just written
     t0 = time.time()
     r = subprocess.run([os.path.join(ROOT, "pais-mvs_b200", "bin", "tmvs"), "-f", os.path.join(d, "exp.mvs"), "--config",
