@@ -67,7 +67,7 @@ int main(int argc, char **argv) {
     int roundSize = 1024, device = 0, gpus = 1;
     unsigned long long seed = 42;
     double autosave = 5.0;
-    bool expand = true, verbose = false, mergeSlots = false;
+    bool expand = true, verbose = false, mergeSlots = true;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if ((a == "-r" || a == "-f" || a == "-v" || a == "-a") && i + 1 < argc) { mode = a; input = argv[++i]; }

@@ -5,8 +5,9 @@
  *
  * Kept from the reference: MvsConfig (byte-identical, mvs.h:19-72), the NVM / NVM2 / MVS_V2 / MVS_V3 input formats, the
  * MVS_V3 / PLY / PSR output formats, config.txt, compiled defaults, seed refinement, cell maps, runtime filtering,
- * expansion strategies. Changed on purpose: expansion runs in ROUNDS (pop K parents, generate all their candidates,
- * refine the batch on the GPU, commit serially in parent order) instead of one patch at a time;
+ * expansion strategies. Changed on purpose: expansion runs in ROUNDS (pop K parents, generate their candidates — the
+ * cells a candidate is expected to fill are not targeted again in the round —, refine the batch on the GPU, commit
+ * serially in slot / parent order with every target cell re-checked) instead of one patch at a time;
  * images are read as PGM/PPM (no OpenCV here; tools/convert_images.py makes them).
  */
 #ifndef TMVS_HOST_H
@@ -83,7 +84,7 @@ public:
     std::vector<int> queue;            /* insertion order (the reference's container) */
     int nextId = 0;
     int roundSize = 1024;              /* parents popped per expansion round */
-    bool mergeSlots = false;           /* one GPU pass per round over all camera slots (expected-neighbour prediction) instead of one per slot */
+    bool mergeSlots = true;            /* one GPU pass per round over all camera slots (expected-neighbour prediction); false: one per slot */
     int device = 0;                    /* first device */
     int numGpus = 1;                   /* devices device .. device+numGpus-1, candidates sharded by index */
     uint64_t rngSeed = 42;

@@ -654,6 +654,18 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     double tPop = 0, tGen = 0, tCommit = 0, tSave = 0;
     Clock::time_point lastSave = Clock::now();
     long gpuCalls = 0, refinedMax = 0;
+    /* per-pass scratch over the cell maps, reset lazily by a pass stamp: candidates already generated for a cell, and
+     * (merged mode) the chain of candidates expected to land in it */
+    struct CellScratch { std::vector<int> stamp, pend, head; };
+    std::vector<CellScratch> scratch(cameras.size());
+    for (size_t i = 0; i < cameras.size(); ++i) {
+        const size_t nc = (size_t)cellMaps[i].width * cellMaps[i].height;
+        scratch[i].stamp.assign(nc, -1);
+        scratch[i].pend.assign(nc, 0);
+        scratch[i].head.assign(nc, -1);
+    }
+    std::vector<std::pair<int, int> > chain;       /* (candidate index, next entry) */
+    int passStamp = 0;
     for (int round = 0;; ++round) {
         /* 1. pop up to roundSize parents in strategy order */
         Clock::time_point tp0 = Clock::now();
@@ -672,8 +684,10 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
         /* 2.-4. The reference visits a parent's visible cameras one after the other (expandNeighborCell,
          * mvs.cpp:535-563) and inserts each refined candidate before looking at the next camera, so the (up to) five
          * views of the same 3-D neighbour are refined once: the first one fills the cells the others would target.
-         * A round therefore runs one pass per camera slot i: candidates of slot i for all parents -> GPU -> serial
-         * commit in parent order -> slot i+1 sees the updated cell maps. */
+         * Refining every candidate of every slot blindly would refine that neighbour five times (2.7x the work).
+         * --slot-passes: one pass per camera slot i — candidates of slot i for all parents -> GPU -> serial commit in
+         * parent order -> slot i+1 sees the updated cell maps (the reference's visiting order; the passes of slots 1..
+         * are sparse, each paying a full kernel latency). Default (mergeSlots): one pass, see below. */
         size_t nCands = 0, accepted = 0;
         size_t maxSlots = 0;
         for (size_t k = 0; k < parents.size(); ++k) {
@@ -688,7 +702,6 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
          * the centre across a cell border, or the expected patch was rejected) cost a wasted refinement or leave a cell
          * to a later round; the commit below still re-checks every target cell against the real state. The sparse
          * passes of slots 1.. (tens of candidates, a full kernel latency each) disappear: 5x fewer, 5x larger calls. */
-        std::map<std::pair<int, std::pair<int, int> >, std::vector<int> > expected;   /* cell -> indices into cpatch (merged mode) */
         for (size_t slot0 = 0; slot0 < maxSlots; slot0 = mergeSlots ? maxSlots : slot0 + 1) {
             const size_t slot1 = mergeSlots ? maxSlots : slot0 + 1;
             Clock::time_point tg0 = Clock::now();
@@ -697,7 +710,14 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             std::vector<std::vector<int> > parentCams;
             /* a cell can take at most maxCellPatchNum patches (skipNeighborCell, mvs.cpp:794-795): do not refine more
              * candidates for a cell than it still has room for — the serial reference would have skipped them */
-            std::map<std::pair<int, std::pair<int, int> >, int> pending;
+            ++passStamp;
+            chain.clear();
+            auto cellAt = [&](int cam, int x, int y) -> size_t {
+                const size_t idx = (size_t)y * cellMaps[cam].width + x;
+                CellScratch &sc = scratch[cam];
+                if (sc.stamp[idx] != passStamp) { sc.stamp[idx] = passStamp; sc.pend[idx] = 0; sc.head[idx] = -1; }
+                return idx;
+            };
             bool anySlot = false;
             for (size_t slot = slot0; slot < slot1; ++slot)
             for (size_t k = 0; k < parents.size(); ++k) {
@@ -713,14 +733,13 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 for (int j = 0; j < 4; ++j) {
                     if (!m.inMap(nx[j], ny[j])) continue;
                     if (skipNeighborCell(m.cell(nx[j], ny[j]), pth)) continue;
-                    const std::pair<int, std::pair<int, int> > cellKey = std::make_pair(ci, std::make_pair(nx[j], ny[j]));
-                    int &pend = pending[cellKey];
+                    const size_t cellIdx = cellAt(ci, nx[j], ny[j]);
+                    int &pend = scratch[ci].pend[cellIdx];
                     if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
                     if (mergeSlots) {
-                        std::map<std::pair<int, std::pair<int, int> >, std::vector<int> >::const_iterator ex = expected.find(cellKey);
                         bool taken = false;
-                        if (ex != expected.end())
-                            for (size_t q = 0; q < ex->second.size() && !taken; ++q) taken = isNeighbor(pth, cpatch[ex->second[q]], cfg.neighborRadius);
+                        for (int q = scratch[ci].head[cellIdx]; q >= 0 && !taken; q = chain[q].second)
+                            taken = isNeighbor(pth, cpatch[chain[q].first], cfg.neighborRadius);
                         if (taken) continue;
                     }
                     ++pend;
@@ -739,7 +758,11 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                             double pt[2];
                             const int cv = pth.camIdx[v];
                             if (!cameras[cv].project(e.center, pt, 0, cfg.lodRatio)) continue;
-                            expected[std::make_pair(cv, std::make_pair((int)(pt[0] / cfg.cellSize), (int)(pt[1] / cfg.cellSize)))].push_back((int)cpatch.size() - 1);
+                            const int ex = (int)(pt[0] / cfg.cellSize), ey = (int)(pt[1] / cfg.cellSize);
+                            if (!cellMaps[cv].inMap(ex, ey)) continue;
+                            const size_t eIdx = cellAt(cv, ex, ey);
+                            chain.push_back(std::make_pair((int)cpatch.size() - 1, scratch[cv].head[eIdx]));
+                            scratch[cv].head[eIdx] = (int)chain.size() - 1;
                         }
                 }
             }
