@@ -50,6 +50,17 @@ def test_reconstruct_plane(tmp_path):
     os.makedirs(d2)
     run_tmvs(d, path, ["--round", "64", "--out-dir", d2])
     assert open(os.path.join(d, "exp.mvs"), "rb").read() == open(os.path.join(d2, "exp.mvs"), "rb").read()
+    # --slot-passes (one GPU pass per camera slot, the reference's visiting order) grows the same surface as the default
+    # merged pass: same coverage to a few per cent, same accuracy
+    d3 = os.path.join(d, "slots")
+    os.makedirs(d3)
+    out_s = run_tmvs(d, path, ["--round", "64", "--slot-passes", "--out-dir", d3])
+    _, _, exp_s = mvsio.read_mvs(os.path.join(d3, "exp.mvs"))
+    assert abs(len(exp_s) - len(exp)) <= 0.05 * len(exp), (len(exp_s), len(exp))
+    zs = np.array([p["center"][2] for p in exp_s])
+    assert np.percentile(np.abs(zs - sc.plane_z), 95) < 5e-3
+    calls = lambda txt: int(txt.split("gpu calls ")[1].split()[0])
+    assert calls(out) < calls(out_s)                                     # fewer, larger calls
     # warm start from the MVS file (TMVS.cpp:87-89): loads cameras + patches and re-refines them as seeds
     out3 = run_tmvs(d, os.path.join(d, "seed.mvs"), ["--no-expand", "--out-dir", d2])
     assert "seeds kept" in out3
