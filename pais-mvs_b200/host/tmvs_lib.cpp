@@ -718,6 +718,25 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 if (sc.stamp[idx] != passStamp) { sc.stamp[idx] = passStamp; sc.pend[idx] = 0; sc.head[idx] = -1; }
                 return idx;
             };
+            /* the read-only part of the visit — is the neighbour cell inside the map and not to be skipped
+             * (skipNeighborCell, mvs.cpp:792-807: the patch look-ups and isNeighbor tests) — for every (parent, slot,
+             * neighbour) on all host cores; the order-dependent part below stays serial */
+            const size_t nSl = slot1 - slot0;
+            std::vector<unsigned char> open(parents.size() * nSl * 4, 0);
+#pragma omp parallel for schedule(dynamic, 32) if (parents.size() >= 128)
+            for (long k = 0; k < (long)parents.size(); ++k) {
+                std::map<int, Patch>::const_iterator pit = patches.find(parents[k]);
+                if (pit == patches.end()) continue;
+                const Patch &pth = pit->second;
+                for (size_t slot = slot0; slot < slot1; ++slot) {
+                    if (slot >= pth.camIdx.size() || 2 * slot + 1 >= pth.imgPoint.size()) continue;
+                    const CellMap &m = cellMaps[pth.camIdx[slot]];
+                    const int cx = (int)(pth.imgPoint[2 * slot] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * slot + 1] / cfg.cellSize);
+                    const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
+                    for (int j = 0; j < 4; ++j)
+                        open[((size_t)k * nSl + (slot - slot0)) * 4 + j] = m.inMap(nx[j], ny[j]) && !skipNeighborCell(m.cell(nx[j], ny[j]), pth);
+                }
+            }
             bool anySlot = false;
             for (size_t slot = slot0; slot < slot1; ++slot)
             for (size_t k = 0; k < parents.size(); ++k) {
@@ -731,8 +750,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 const int cx = (int)(pth.imgPoint[2 * slot] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * slot + 1] / cfg.cellSize);
                 const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
                 for (int j = 0; j < 4; ++j) {
-                    if (!m.inMap(nx[j], ny[j])) continue;
-                    if (skipNeighborCell(m.cell(nx[j], ny[j]), pth)) continue;
+                    if (!open[(k * nSl + (slot - slot0)) * 4 + j]) continue;
                     const size_t cellIdx = cellAt(ci, nx[j], ny[j]);
                     int &pend = scratch[ci].pend[cellIdx];
                     if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
