@@ -39,24 +39,38 @@ static int runFiltering(MVS &mvs, const std::string &file, const std::string &ou
         return 1;
     }
     printf("patches: %zu\n", mvs.patches.size());
-    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    typedef std::chrono::steady_clock Clock;
+    const Clock::time_point t0 = Clock::now();
+    double tFilter = 0, tWrite = 0;
+    Clock::time_point t = t0;
+    auto lap = [&](double &acc) { const Clock::time_point n = Clock::now(); acc += std::chrono::duration<double>(n - t).count(); t = n; };
     mvs.cellFiltering();
+    lap(tFilter);
     mvs.writeMVS((outDir + "PMVS_filter1.mvs").c_str());
     mvs.writePLY((outDir + "PMVS_filter1.ply").c_str());
+    lap(tWrite);
     mvs.visibilityFiltering();
+    lap(tFilter);
     mvs.writeMVS((outDir + "PMVS_filter2.mvs").c_str());
     mvs.writePLY((outDir + "PMVS_filter2.ply").c_str());
+    lap(tWrite);
     mvs.neighborCellFiltering(0.25);
+    lap(tFilter);
     mvs.writeMVS((outDir + "PMVS_filter3.mvs").c_str());
     mvs.writePLY((outDir + "PMVS_filter3.ply").c_str());
     mvs.writeDeletedPatchMVS((outDir + "PMVS_filter_deleted.mvs").c_str());
     mvs.writeDeletedPatchPLY((outDir + "PMVS_filter_deleted.ply").c_str());
     mvs.clearDeletedPatches();
+    lap(tWrite);
     if (!mvs.neighborPatchFiltering(0.25)) { fprintf(stderr, "PCMVS filter failed: %s\n", mvs.lastError().c_str()); return 1; }
+    double tPair = 0;
+    lap(tPair);
     mvs.writeMVS((outDir + "PCMVS_filter.mvs").c_str());
     mvs.writePLY((outDir + "PCMVS_filter.ply").c_str());
     mvs.writeDeletedPatchMVS((outDir + "PCMVS_filter_deleted.mvs").c_str());
     mvs.writeDeletedPatchPLY((outDir + "PCMVS_filter_deleted.ply").c_str());
+    lap(tWrite);
+    printf("phase seconds: PMVS filters %.3f PCMVS filter %.3f (incl. CUDA context) output %.3f\n", tFilter, tPair, tWrite);
     printf("patches kept: %zu\n", mvs.patches.size());
     printf("time1\t%f\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     return 0;
