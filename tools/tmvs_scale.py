@@ -18,7 +18,11 @@ cfg = abi.readme_config()
 cfg.maxLOD = 2
 cfg.cellSize = cell
 sc = scene.SynthScene(cfg, nviews=5, width=w, height=h, seed=1234)
-with tempfile.TemporaryDirectory() as d:
+keep = os.environ.get("TMVS_SCALE_DIR")            # keep the dataset and the outputs there (profiling tmvs directly afterwards)
+if keep:
+    os.makedirs(keep, exist_ok=True)
+with (tempfile.TemporaryDirectory() if not keep else open(os.devnull)) as _d:
+    d = keep or _d
     path = mvsio.write_nvm_scene(d, sc, n_seeds=64)
     mvsio.write_config(os.path.join(d, "config.txt"), cfg)
     t0 = time.time()
