@@ -157,6 +157,12 @@ int main(int argc, char **argv) {
     const Clock::time_point t3 = Clock::now();
     const double total = std::chrono::duration<double>(t3 - t0).count();
     printf("patches: %zu refined: %ld gpu_seconds: %f\n", mvs.patches.size(), mvs.refinedCount, mvs.gpuSeconds);
+    if (mvs.refinedCount > 0)
+        printf("per refined patch: evaluations %.1f (window loop %.1f) iterations %.1f runs %.2f views kept %.2f dropped %.1f %% LOD 0/1/2/3+ %ld/%ld/%ld/%ld\n",
+               (double)mvs.statEvaluations / mvs.refinedCount, (double)mvs.statWindowEvaluations / mvs.refinedCount,
+               (double)mvs.statIterations / mvs.refinedCount, (double)mvs.statRuns / mvs.refinedCount, (double)mvs.statViews / mvs.refinedCount,
+               100.0 * mvs.statDropped / mvs.refinedCount, mvs.statLOD[0], mvs.statLOD[1], mvs.statLOD[2],
+               mvs.statLOD[3] + mvs.statLOD[4] + mvs.statLOD[5] + mvs.statLOD[6] + mvs.statLOD[7]);
     printf("phase seconds: seeds %.3f (context %.3f) expansion %.3f output %.3f\n", std::chrono::duration<double>(t1 - t0).count(),
            mvs.contextSeconds, std::chrono::duration<double>(t2 - t1).count(), std::chrono::duration<double>(t3 - t2).count());
     printf("time1\t%f\n", total);                            /* TMVS.cpp:118-119 */

@@ -93,6 +93,9 @@ public:
     std::string imageDir;              /* prefix for camera image files */
     long refinedCount = 0;             /* patches sent through refine() */
     double gpuSeconds = 0;             /* inside pmvs_refine_batch calls */
+    /* what the refined patches cost (sums over PmvsPatchOut): swarm evaluations, evaluations that ran the window loop,
+     * iterations, swarm runs, dropped records, visible cameras kept, level of detail */
+    long statEvaluations = 0, statWindowEvaluations = 0, statIterations = 0, statRuns = 0, statDropped = 0, statViews = 0, statLOD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double contextSeconds = 0;         /* pmvs_create: CUDA context, module load, pyramid upload + build */
 
     explicit MVS(const MvsConfig &c);

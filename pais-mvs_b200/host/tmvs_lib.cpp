@@ -613,6 +613,13 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
         p.LOD = o.LOD;
         p.refCamIdx = o.refCamIdx;
         p.drop = o.drop != 0;
+        statEvaluations += o.evaluations;
+        statWindowEvaluations += o.windowEvaluations;
+        statIterations += o.psoIterations;
+        statRuns += o.psoRuns;
+        statDropped += o.drop != 0;
+        statViews += o.nCam;
+        if (o.LOD >= 0 && o.LOD < 8) statLOD[o.LOD]++;
         p.camIdx.assign(o.camIdx, o.camIdx + o.nCam);
         p.imgPoint.resize((size_t)o.nImgPoint * 2);
         for (int k = 0; k < o.nImgPoint; ++k) { p.imgPoint[2 * k] = o.imgPoint[k][0]; p.imgPoint[2 * k + 1] = o.imgPoint[k][1]; }
