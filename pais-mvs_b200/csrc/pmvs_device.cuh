@@ -972,7 +972,24 @@ __device__ __noinline__ double warp_window(const DevScene &S, const EvalCtx &E, 
         else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
         else if (VCAP == 0 && nx > 0 && E.refView >= 0) fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
-    } else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    } else {
+        /* Exact early-out. The four window corners are window samples: if the reference pixel of one is not masked
+         * (patch.cpp:986) and some view's sample there fails the bounds test (:999), the reference returns DBL_MAX
+         * whatever the other pixels hold — and so would the checked loop below, after walking the whole window at a
+         * third of the unchecked loop's speed. Near the image borders most failed corner tests end here (the host
+         * driver's late expansion rounds spent a fifth of their time, and most of their barrier waits, on such walks).
+         * Same sample_view<true> and same (x, y) as the loop: the decision is the loop's own. */
+        bool hit = false;
+        for (int t = lane; t < 4 * E.V; t += 32) {
+            const int v = t >> 2, cidx = t & 3;
+            const double x = W.xs[(cidx & 1) ? nx - 1 : 0], y = W.ys[(cidx & 2) ? ny - 1 : 0];
+            const size_t rofs = (size_t)__double2int_rn(y) * E.refCols + __double2int_rn(x);
+            double c;
+            if ((__ldg(E.refQuad + rofs) & 0xff) != 0 && !sample_view<true>(W.H + 9 * v, E.view[v], x, y, c)) hit = true;
+        }
+        if (__any_sync(PMVS_FULL, hit)) ok = false;
+        else ok = fitness_samples<VCAP, true>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
+    }
     __syncwarp();
     if (!ok) return DBL_MAX;                                                          /* :999-1002 */
     return fit / sw;                                                                  /* :1046 */
