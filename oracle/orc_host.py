@@ -332,3 +332,41 @@ def recentering(mvs, p):
     p.center = [float(v) for v in x]
     estimated_normal(mvs, p)
     return A, b
+
+
+def expand_neighbor_cell(mvs, p, refine):
+    """MVS::expandNeighborCell + expandCell, TMVS/mvs/mvs.cpp:529-577: every visible camera of the parent in turn, its four
+    neighbour cells (left, up, right, down), each refined candidate inserted before the next cell is looked at.
+    `refine(center, parent)` stands for `Patch(center, parent)` + refine() + removeInvisibleCamera() and returns a Patch."""
+    cs = mvs.cfg.cellSize
+    for i, ci in enumerate(p.cam_idx):
+        cam, cmap = mvs.cameras[ci], mvs.cell_maps[ci]
+        cx, cy = int(p.img_point[i][0] / cs), int(p.img_point[i][1] / cs)
+        for nx, ny in ((cx - 1, cy), (cx, cy - 1), (cx + 1, cy), (cx, cy + 1)):
+            if not cmap.in_map(nx, ny):
+                continue
+            if mvs.skip_neighbor_cell(cmap.map[ny][nx], p):
+                continue
+            mvs.insert_patch(refine(mvs.expansion_patch_center(cam, p, nx, ny), p))
+
+
+def expansion_patches(mvs, refine, reference_loop_exit=False):
+    """MVS::expansionPatches, TMVS/mvs/mvs.cpp:233-275. The reference tests `!queue.empty()` AFTER popping the next id
+    (:241-243, :271), so the patch popped last is never expanded; reference_loop_exit=True keeps that, False expands it
+    too (what the host driver does)."""
+    mvs.set_cell_maps()
+    mvs.init_priority_queue()
+    mvs.set_neighbor_radius()
+    pid = mvs.pop()
+    while (len(mvs.queue) > 0) if reference_loop_exit else (pid >= 0):
+        p = mvs.patches.get(pid)
+        if p is None:               # cannot happen: pops return live ids (the reference would spin here, :246)
+            break
+        p.expanded = True
+        if not mvs.runtime_filtering(p):            # :255-260
+            mvs.delete_patch(pid)
+            pid = mvs.pop()
+            continue
+        expand_neighbor_cell(mvs, p, refine)
+        pid = mvs.pop()
+    mvs.set_neighbor_radius()

@@ -122,6 +122,12 @@ public:
     void clearDeletedPatches() { deletedPatches.clear(); }          /* mvs.cpp:154-156 */
     double lastAvgNeighborNum = 0;                                  /* "average neighbor number", mvs.cpp:506-511 */
 
+    /* tests only: a host stand-in for pmvs_refine_batch, so that the driver's control flow (rounds, candidate generation,
+     * commit order) can be checked on a GPU-less box; never set by tmvs */
+    typedef int (*RefineOverride)(void *user, int n, const PmvsPatchIn *in, PmvsPatchOut *out, unsigned flags);
+    RefineOverride refineOverride = nullptr;
+    void *refineUser = nullptr;
+
     /* pieces exposed for tests */
     bool addCamera(Camera &cam, bool loadImage);
     void reCentering();                                             /* mvs.cpp:135-145, patch.cpp:67-112 */

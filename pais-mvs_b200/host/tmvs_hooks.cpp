@@ -5,6 +5,7 @@
  * tests/test_host_parity_cpu.py can drive them from ctypes against the test suite's restatement of the reference
  * lines. Nothing here is on the product path: `tmvs` does not link this file and no GPU is touched (no context is created).
  */
+#include <cmath>
 #include <cstring>
 
 #include "tmvs.h"
@@ -28,7 +29,70 @@ Patch makePatch(int id, const double *center, const double *normal, double fitne
 }
 }   // namespace
 
+/* Stand-in for Patch::refine() in driver tests: a deterministic function of the candidate alone. The centre slides
+ * along the ray from the first parent camera onto the plane z = planeZ, the normal is (0,0,-1), every camera sees the
+ * patch, and the priority varies with the position so that the queue strategies have something to order. A centre
+ * that leaves a camera's image is dropped. Restated in tests/test_expansion_cpu.py. */
+struct PlaneRefiner {
+    MVS *mvs;
+    double planeZ;
+    long calls = 0, refined = 0;
+};
+int planeRefine(void *user, int n, const PmvsPatchIn *in, PmvsPatchOut *out, unsigned) {
+    PlaneRefiner &r = *(PlaneRefiner *)user;
+    const MVS &m = *r.mvs;
+    r.calls++;
+    r.refined += n;
+    for (int i = 0; i < n; ++i) {
+        PmvsPatchOut &o = out[i];
+        memset(&o, 0, sizeof(o));
+        const double *C = m.cameras[in[i].camIdx[0]].center;
+        const double t = (r.planeZ - C[2]) / (in[i].center[2] - C[2]);
+        for (int k = 0; k < 3; ++k) o.center[k] = C[k] + t * (in[i].center[k] - C[k]);
+        o.normal[0] = 0; o.normal[1] = 0; o.normal[2] = -1;
+        o.normalS[0] = acos(-1.0); o.normalS[1] = 0;
+        o.fitness = 1.0;
+        o.correlation = 0.95;
+        o.priority = 1.0 + (o.center[0] * 0.37 + o.center[1] * 0.11);
+        o.LOD = 0;
+        o.refCamIdx = in[i].camIdx[0];
+        o.psoRuns = 1;
+        o.nCam = (int)m.cameras.size();
+        o.nImgPoint = o.nCam;
+        for (int c = 0; c < o.nCam; ++c) {
+            o.camIdx[c] = (uint16_t)c;
+            if (!m.cameras[c].project(o.center, o.imgPoint[c], 0, m.cfg.lodRatio)) o.drop = 1;
+        }
+        if (o.drop) { o.fitness = o.priority = 1.7976931348623157e308; o.nImgPoint = 0; }
+    }
+    return PMVS_OK;
+}
+
 extern "C" {
+
+/* runs MVS::expansionPatches over the patches put so far with the plane stand-in; returns the number of refine calls */
+long tmvs_hook_expand_plane(void *h, double planeZ, int roundSize, int mergeSlots, long *refined) {
+    MVS &m = *(MVS *)h;
+    PlaneRefiner r;
+    r.mvs = &m;
+    r.planeZ = planeZ;
+    m.refineOverride = planeRefine;
+    m.refineUser = &r;
+    m.roundSize = roundSize;
+    m.mergeSlots = mergeSlots != 0;
+    m.autosaveSeconds = 1e18;
+    const bool ok = m.expansionPatches();
+    m.refineOverride = nullptr;
+    m.refineUser = nullptr;
+    if (refined) *refined = r.refined;
+    return ok ? r.calls : -1;
+}
+int tmvs_hook_patch_ids(void *h, int *out, int cap) {
+    const MVS &m = *(MVS *)h;
+    int k = 0;
+    for (std::map<int, Patch>::const_iterator it = m.patches.begin(); it != m.patches.end() && k < cap; ++it) out[k++] = it->first;
+    return (int)m.patches.size();
+}
 
 void *tmvs_hook_create(const PmvsConfig *cfg) { return new MVS(*cfg); }
 void tmvs_hook_destroy(void *h) { delete (MVS *)h; }
@@ -65,6 +129,7 @@ void tmvs_hook_put_patch(void *h, int id, const double *center, const double *no
                          int nCam, const int *camIdx, const double *imgPoint, int expanded) {
     MVS &m = *(MVS *)h;
     m.patches[id] = makePatch(id, center, normal, fitness, priority, correlation, nCam, camIdx, imgPoint, expanded, 0);
+    if (m.nextId <= id) m.nextId = id + 1;      /* the loaders number patches with nextId++ */
 }
 void tmvs_hook_set_cell_maps(void *h) { ((MVS *)h)->setCellMaps(); }
 void tmvs_hook_init_queue(void *h) {   /* initPriorityQueue, mvs.cpp:90-95: every patch in id order */

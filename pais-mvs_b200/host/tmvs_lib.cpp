@@ -511,7 +511,7 @@ int MVS::getPatchIdFromQueue() {
 /* --- GPU ------------------------------------------------------------------------------------------------ */
 /* one context per GPU: the scene (cameras, pyramids, tables) is replicated, patches are sharded */
 bool MVS::ensureContext() {
-    if (!ctxs.empty()) return true;
+    if (!ctxs.empty() || refineOverride) return true;
     std::vector<PmvsCamera> recs(cameras.size());
     for (size_t i = 0; i < cameras.size(); ++i) {
         const Camera &c = cameras[i];
@@ -588,7 +588,9 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
     /* contiguous shards, one host thread per GPU; results do not depend on the split (the PSO stream is keyed by patch id) */
     const int G = (int)ctxs.size();
     std::vector<int> rcs(G, PMVS_OK);
-    if (G == 1 || n < 2 * G) rcs[0] = pmvs_refine_batch(ctxs[0], n, in.data(), out.data(), flags);
+    if (refineOverride) {             /* CPU tests of the driver's control flow: a stand-in for the library call */
+        rcs.assign(1, refineOverride(refineUser, n, in.data(), out.data(), flags));
+    } else if (G == 1 || n < 2 * G) rcs[0] = pmvs_refine_batch(ctxs[0], n, in.data(), out.data(), flags);
     else {
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g) {
@@ -598,8 +600,8 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
         for (int g = 0; g < G; ++g) th[g].join();
     }
     gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    for (int g = 0; g < G; ++g)
-        if (rcs[g] != PMVS_OK) { err = std::string("pmvs_refine_batch: ") + pmvs_last_error(ctxs[g]); return false; }
+    for (size_t g = 0; g < rcs.size(); ++g)
+        if (rcs[g] != PMVS_OK) { err = std::string("pmvs_refine_batch: ") + (refineOverride ? "stand-in failed" : pmvs_last_error(ctxs[g])); return false; }
     refinedCount += n;
     for (int i = 0; i < n; ++i) {
         Patch &p = *batch[i];
@@ -673,11 +675,20 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     }
     std::vector<std::pair<int, int> > chain;       /* (candidate index, next entry) */
     int passStamp = 0;
+    /* merged mode: parents whose expectation failed (a candidate of theirs was rejected) try their remaining
+     * (slot, neighbour) combinations in the next round's pass, like the serial reference moves on to the next camera */
+    struct Carry { int parent; std::vector<unsigned char> tried; };
+    std::vector<Carry> carry;
     for (int round = 0;; ++round) {
         /* 1. pop up to roundSize parents in strategy order */
         Clock::time_point tp0 = Clock::now();
         std::vector<int> parents;
-        while ((int)parents.size() < roundSize) {
+        std::vector<std::vector<unsigned char> > tried;     /* per parent: (slot, neighbour) combinations already refined */
+        for (size_t k = 0; k < carry.size(); ++k)
+            if (patches.find(carry[k].parent) != patches.end()) { parents.push_back(carry[k].parent); tried.push_back(carry[k].tried); }
+        carry.clear();
+        const size_t nCarried = parents.size();
+        while ((int)(parents.size() - nCarried) < roundSize) {
             const int id = getPatchIdFromQueue();
             if (id < 0) break;
             std::map<int, Patch>::iterator it = patches.find(id);
@@ -709,10 +720,15 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
          * the centre across a cell border, or the expected patch was rejected) cost a wasted refinement or leave a cell
          * to a later round; the commit below still re-checks every target cell against the real state. The sparse
          * passes of slots 1.. (tens of candidates, a full kernel latency each) disappear: 5x fewer, 5x larger calls. */
+        tried.resize(parents.size());
+        for (size_t k = 0; k < parents.size(); ++k) tried[k].resize(maxSlots * 4, 0);
+        std::vector<int> nGenerated(parents.size(), 0), nRejected(parents.size(), 0);
+        std::vector<int> candParentIdx;
         for (size_t slot0 = 0; slot0 < maxSlots; slot0 = mergeSlots ? maxSlots : slot0 + 1) {
             const size_t slot1 = mergeSlots ? maxSlots : slot0 + 1;
             Clock::time_point tg0 = Clock::now();
             std::vector<Cand> cands;
+            candParentIdx.clear();
             std::vector<Patch> cpatch;
             std::vector<std::vector<int> > parentCams;
             /* a cell can take at most maxCellPatchNum patches (skipNeighborCell, mvs.cpp:794-795): do not refine more
@@ -758,6 +774,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
                 for (int j = 0; j < 4; ++j) {
                     if (!open[(k * nSl + (slot - slot0)) * 4 + j]) continue;
+                    if (tried[k][slot * 4 + j]) continue;
                     const size_t cellIdx = cellAt(ci, nx[j], ny[j]);
                     int &pend = scratch[ci].pend[cellIdx];
                     if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
@@ -775,6 +792,9 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                     memcpy(e.normal, pth.normal, sizeof(e.normal));
                     normal2Spherical(e.normal, e.normalS);
                     const Cand c = {parents[k], ci, nx[j], ny[j]};
+                    tried[k][slot * 4 + j] = 1;
+                    nGenerated[k]++;
+                    candParentIdx.push_back((int)k);
                     cands.push_back(c);
                     cpatch.push_back(e);
                     parentCams.push_back(pth.camIdx);
@@ -809,10 +829,14 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 const size_t before = patches.size();
                 insertPatch(cpatch[k]);
                 accepted += patches.size() - before;
+                if (patches.size() == before) nRejected[candParentIdx[k]]++;      /* runtimeFiltering turned it down */
             }
             nCands += cands.size();
             tCommit += std::chrono::duration<double>(Clock::now() - tc0).count();
         }
+        if (mergeSlots)
+            for (size_t k = 0; k < parents.size(); ++k)
+                if (nRejected[k] > 0 && nGenerated[k] > 0) { Carry c; c.parent = parents[k]; c.tried.swap(tried[k]); carry.push_back(c); }
         if (verbose)
             printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), nCands, accepted,
                    patches.size(), byPriorityQueueSize());
