@@ -1,5 +1,6 @@
 """End-to-end timing of `tmvs -r` on a synthetic NVM scene: how much of the wall clock is GPU refinement vs the host's
 serial commit (the expected scaling limit). usage: python tools/tmvs_scale.py [width height round cell [extra tmvs -r switches ...]]"""
+import contextlib
 import os
 import subprocess
 import sys
@@ -21,8 +22,7 @@ sc = scene.SynthScene(cfg, nviews=5, width=w, height=h, seed=1234)
 keep = os.environ.get("TMVS_SCALE_DIR")            # keep the dataset and the outputs there (profiling tmvs directly afterwards)
 if keep:
     os.makedirs(keep, exist_ok=True)
-with (tempfile.TemporaryDirectory() if not keep else open(os.devnull)) as _d:
-    d = keep or _d
+with (contextlib.nullcontext(keep) if keep else tempfile.TemporaryDirectory()) as d:
     path = mvsio.write_nvm_scene(d, sc, n_seeds=64)
     mvsio.write_config(os.path.join(d, "config.txt"), cfg)
     t0 = time.time()
