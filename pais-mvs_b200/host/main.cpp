@@ -62,6 +62,7 @@ static int runFiltering(MVS &mvs, const std::string &file, const std::string &ou
     mvs.writeDeletedPatchPLY((outDir + "PMVS_filter_deleted.ply").c_str());
     mvs.clearDeletedPatches();
     lap(tWrite);
+    printf("phase seconds: PMVS filters %.3f output %.3f\n", tFilter, tWrite);
     if (!mvs.neighborPatchFiltering(0.25)) { fprintf(stderr, "PCMVS filter failed: %s\n", mvs.lastError().c_str()); return 1; }
     double tPair = 0;
     lap(tPair);
@@ -70,7 +71,7 @@ static int runFiltering(MVS &mvs, const std::string &file, const std::string &ou
     mvs.writeDeletedPatchMVS((outDir + "PCMVS_filter_deleted.mvs").c_str());
     mvs.writeDeletedPatchPLY((outDir + "PCMVS_filter_deleted.ply").c_str());
     lap(tWrite);
-    printf("phase seconds: PMVS filters %.3f PCMVS filter %.3f (incl. CUDA context) output %.3f\n", tFilter, tPair, tWrite);
+    printf("phase seconds: PCMVS filter %.3f (incl. CUDA context) output %.3f (all eight files)\n", tPair, tWrite);
     printf("patches kept: %zu\n", mvs.patches.size());
     printf("time1\t%f\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     return 0;

@@ -147,6 +147,21 @@ public:
     void queueClear();
 
 private:
+    /* id -> patch while a filter runs (std::map nodes do not move; deletePatch clears the entry, insertPatch drops the
+     * index): the cell walks of mvs.cpp:279-446 look every cell member up, millions of times */
+    mutable std::vector<const Patch *> idIndex;
+    struct IdIndexGuard {
+        const MVS &m;
+        explicit IdIndexGuard(const MVS &mvs);
+        ~IdIndexGuard() { m.idIndex.clear(); }
+    };
+    const Patch *lookup(int id) const {
+        if (idIndex.empty()) {
+            std::map<int, Patch>::const_iterator it = patches.find(id);
+            return it == patches.end() ? nullptr : &it->second;
+        }
+        return id >= 0 && (size_t)id < idIndex.size() ? idIndex[id] : nullptr;
+    }
     std::set<std::pair<std::pair<double, long>, int> > prioQueue;
     std::deque<int> fifo;
     long queueSeq = 0;

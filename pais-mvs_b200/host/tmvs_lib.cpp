@@ -446,6 +446,7 @@ void MVS::setCellMaps() {   /* mvs.cpp:116-133 (+ initCellMaps :74-88) */
 
 void MVS::insertPatch(const Patch &p) {   /* mvs.cpp:579-601 */
     if (!runtimeFiltering(p)) return;
+    idIndex.clear();
     patches.insert(std::pair<int, Patch>(p.id, p));
     queuePush(p.id);
     for (size_t i = 0; i < p.camIdx.size() && 2 * i + 1 < p.imgPoint.size(); ++i)
@@ -461,6 +462,7 @@ void MVS::deletePatch(int id) {   /* mvs.cpp:607-634 */
             cellMaps[p.camIdx[i]].drop((int)(p.imgPoint[2 * i] / cfg.cellSize), (int)(p.imgPoint[2 * i + 1] / cfg.cellSize), p.id);
     }
     deletedPatches.push_back(it->second);
+    if (id >= 0 && (size_t)id < idIndex.size()) idIndex[id] = nullptr;
     patches.erase(it);
 }
 
@@ -859,6 +861,14 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
 /* ---------------------------------------------------------------------------------------------------------
  * `-f` filters (mvs.cpp:279-525)
  * ------------------------------------------------------------------------------------------------------- */
+MVS::IdIndexGuard::IdIndexGuard(const MVS &mvs) : m(mvs) {
+    m.idIndex.clear();
+    if (m.patches.empty()) return;
+    m.idIndex.assign((size_t)m.patches.rbegin()->first + 1, nullptr);
+    for (std::map<int, Patch>::const_iterator it = m.patches.begin(); it != m.patches.end(); ++it)
+        if (it->first >= 0) m.idIndex[it->first] = &it->second;
+}
+
 void MVS::ensureFilterMaps() {   /* mvs.cpp:280-283, :328-331, :400-403, :449-452 */
     if (cellMaps.empty()) {
         setNeighborRadius();
@@ -868,6 +878,7 @@ void MVS::ensureFilterMaps() {   /* mvs.cpp:280-283, :328-331, :400-403, :449-45
 
 void MVS::cellFiltering() {   /* mvs.cpp:279-325 */
     ensureFilterMaps();
+    IdIndexGuard index(*this);
     for (size_t i = 0; i < cameras.size(); ++i) {
         CellMap &map = cellMaps[i];
         for (int x = 0; x < map.width; ++x)
@@ -879,13 +890,13 @@ void MVS::cellFiltering() {   /* mvs.cpp:279-325 */
                     double corrSum = 0;
                     for (int k = 0; k < pthNum; ++k) {
                         if (j == k) continue;
-                        std::map<int, Patch>::const_iterator pk = patches.find(cell[k]);
-                        if (pk == patches.end()) continue;
-                        corrSum += pk->second.correlation;
+                        const Patch *pk = lookup(cell[k]);
+                        if (!pk) continue;
+                        corrSum += pk->correlation;
                     }
-                    std::map<int, Patch>::const_iterator pj = patches.find(cell[j]);
-                    if (pj == patches.end()) continue;
-                    if (pj->second.correlation * (double)pj->second.camIdx.size() < corrSum) removeIdx.push_back(cell[j]);
+                    const Patch *pj = lookup(cell[j]);
+                    if (!pj) continue;
+                    if (pj->correlation * (double)pj->camIdx.size() < corrSum) removeIdx.push_back(cell[j]);
                 }
                 for (size_t j = 0; j < removeIdx.size(); ++j) deletePatch(removeIdx[j]);
             }
@@ -894,6 +905,7 @@ void MVS::cellFiltering() {   /* mvs.cpp:279-325 */
 
 void MVS::neighborCellFiltering(double neighborRatio) {   /* mvs.cpp:327-397 */
     ensureFilterMaps();
+    IdIndexGuard index(*this);
     for (size_t i = 0; i < cameras.size(); ++i) {
         CellMap &map = cellMaps[i];
         for (int x = 0; x < map.width; ++x)
@@ -904,18 +916,18 @@ void MVS::neighborCellFiltering(double neighborRatio) {   /* mvs.cpp:327-397 */
                 const int ny[9] = {y, y - 1, y - 1, y + 1, y + 1, y, y + 1, y, y - 1};
                 const int pthNum = (int)cell.size();
                 for (int j = 0; j < pthNum; ++j) {
-                    std::map<int, Patch>::const_iterator pc = patches.find(cell[j]);
-                    if (pc == patches.end()) continue;
-                    const Patch &centerPth = pc->second;
+                    const Patch *pc = lookup(cell[j]);
+                    if (!pc) continue;
+                    const Patch &centerPth = *pc;
                     int neighborPthSum = 0, neighborPthNum = 0;
                     for (int q = 0; q < 9; ++q) {
                         if (!map.inMap(nx[q], ny[q])) continue;
                         const std::vector<int> &neighborCell = map.cell(nx[q], ny[q]);
                         neighborPthSum += (int)neighborCell.size();
                         for (size_t k = 0; k < neighborCell.size(); ++k) {
-                            std::map<int, Patch>::const_iterator pn = patches.find(neighborCell[k]);
-                            if (pn == patches.end()) continue;
-                            if (isNeighbor(centerPth, pn->second, cfg.neighborRadius)) ++neighborPthNum;
+                            const Patch *pn = lookup(neighborCell[k]);
+                            if (!pn) continue;
+                            if (isNeighbor(centerPth, *pn, cfg.neighborRadius)) ++neighborPthNum;
                         }
                     }
                     if ((double)neighborPthNum / (double)neighborPthSum < neighborRatio) removeIdx.push_back(centerPth.id);
@@ -927,6 +939,7 @@ void MVS::neighborCellFiltering(double neighborRatio) {   /* mvs.cpp:327-397 */
 
 void MVS::visibilityFiltering() {   /* mvs.cpp:399-446 */
     ensureFilterMaps();
+    IdIndexGuard index(*this);
     for (std::map<int, Patch>::iterator it = patches.begin(); it != patches.end();) {
         const Patch &pth = it->second;
         const int camNum = (int)pth.camIdx.size();
@@ -941,9 +954,9 @@ void MVS::visibilityFiltering() {   /* mvs.cpp:399-446 */
             const std::vector<int> &cell = map.cell(cx, cy);
             for (size_t p = 0; p < cell.size(); ++p) {
                 if (cell[p] == pth.id) continue;
-                std::map<int, Patch>::const_iterator pn = patches.find(cell[p]);
-                if (pn == patches.end()) continue;
-                const double e[3] = {pn->second.center[0] - cam.center[0], pn->second.center[1] - cam.center[1], pn->second.center[2] - cam.center[2]};
+                const Patch *pn = lookup(cell[p]);
+                if (!pn) continue;
+                const double e[3] = {pn->center[0] - cam.center[0], pn->center[1] - cam.center[1], pn->center[2] - cam.center[2]};
                 const double neighborDepth = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
                 if (depth > neighborDepth) { --visibleCount; break; }
             }
@@ -1030,18 +1043,26 @@ bool MVS::writeDeletedPatchMVS(const char *fileName) const {   /* filewriter.cpp
     return (bool)file;
 }
 
+/* one vertex line of filewriter.cpp:128-135: `file << double` with the default ostream state is printf's %g (precision
+ * 6), the colour goes out r g b from the b,g,r pixel. Formatted into one buffer per file instead of nine stream
+ * insertions per patch (tests/test_host_cpu.py compares the bytes). */
+static void plyLine(std::string &buf, const Patch &p) {
+    char line[256];
+    const int n = snprintf(line, sizeof(line), "%g %g %g %g %g %g %d %d %d\n", p.center[0], p.center[1], p.center[2], p.normal[0], p.normal[1],
+                           p.normal[2], int(p.color[2]), int(p.color[1]), int(p.color[0]));
+    buf.append(line, (size_t)n);
+}
+
 bool MVS::writeDeletedPatchPLY(const char *fileName) const {   /* filewriter.cpp:206-241 */
     std::ofstream file(fileName);
     if (!file.is_open()) return false;
     file << "ply\nformat ascii 1.0\nelement vertex " << deletedPatches.size() << "\n";
     file << "property float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n";
     file << "property uchar diffuse_red\nproperty uchar diffuse_green\nproperty uchar diffuse_blue\nend_header\n";
-    for (size_t i = 0; i < deletedPatches.size(); ++i) {
-        const Patch &p = deletedPatches[i];
-        file << p.center[0] << " " << p.center[1] << " " << p.center[2] << " ";
-        file << p.normal[0] << " " << p.normal[1] << " " << p.normal[2] << " ";
-        file << int(p.color[2]) << " " << int(p.color[1]) << " " << int(p.color[0]) << "\n";
-    }
+    std::string buf;
+    buf.reserve(deletedPatches.size() * 80);
+    for (size_t i = 0; i < deletedPatches.size(); ++i) plyLine(buf, deletedPatches[i]);
+    file.write(buf.data(), (std::streamsize)buf.size());
     return (bool)file;
 }
 
@@ -1247,12 +1268,10 @@ bool MVS::writePLY(const char *fileName) const {   /* filewriter.cpp:104-139 */
     file << "ply\nformat ascii 1.0\nelement vertex " << patches.size() << "\n";
     file << "property float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n";
     file << "property uchar diffuse_red\nproperty uchar diffuse_green\nproperty uchar diffuse_blue\nend_header\n";
-    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) {
-        const Patch &p = it->second;
-        file << p.center[0] << " " << p.center[1] << " " << p.center[2] << " ";
-        file << p.normal[0] << " " << p.normal[1] << " " << p.normal[2] << " ";
-        file << int(p.color[2]) << " " << int(p.color[1]) << " " << int(p.color[0]) << "\n";
-    }
+    std::string buf;
+    buf.reserve(patches.size() * 80);
+    for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) plyLine(buf, it->second);
+    file.write(buf.data(), (std::streamsize)buf.size());
     return (bool)file;
 }
 
