@@ -426,10 +426,10 @@ bool MVS::skipNeighborCell(const std::vector<int> &cell, const Patch &ref) const
     const int n = (int)cell.size();
     if (n >= cfg.maxCellPatchNum) return true;
     for (int k = 0; k < n; ++k) {
-        std::map<int, Patch>::const_iterator it = patches.find(cell[k]);
-        if (it == patches.end()) continue;
-        if (it->second.correlation > cfg.minCorrelation) return true;
-        if (isNeighbor(ref, it->second, cfg.neighborRadius)) return true;
+        const Patch *q = lookup(cell[k]);
+        if (!q) continue;
+        if (q->correlation > cfg.minCorrelation) return true;
+        if (isNeighbor(ref, *q, cfg.neighborRadius)) return true;
     }
     return false;
 }
@@ -446,8 +446,11 @@ void MVS::setCellMaps() {   /* mvs.cpp:116-133 (+ initCellMaps :74-88) */
 
 void MVS::insertPatch(const Patch &p) {   /* mvs.cpp:579-601 */
     if (!runtimeFiltering(p)) return;
-    idIndex.clear();
-    patches.insert(std::pair<int, Patch>(p.id, p));
+    const std::pair<std::map<int, Patch>::iterator, bool> ins = patches.insert(std::pair<int, Patch>(p.id, p));
+    if (!idIndex.empty() && ins.second && p.id >= 0) {        /* keep the id index of a running expansion current */
+        if ((size_t)p.id >= idIndex.size()) idIndex.resize(std::max((size_t)p.id + 1, idIndex.size() * 2), nullptr);
+        idIndex[p.id] = &ins.first->second;
+    }
     queuePush(p.id);
     for (size_t i = 0; i < p.camIdx.size() && 2 * i + 1 < p.imgPoint.size(); ++i)
         cellMaps[p.camIdx[i]].insert((int)(p.imgPoint[2 * i] / cfg.cellSize), (int)(p.imgPoint[2 * i + 1] / cfg.cellSize), p.id);
@@ -655,6 +658,7 @@ bool MVS::refineSeedPatches() {   /* mvs.cpp:196-231 */
 
 bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     setCellMaps();
+    IdIndexGuard index(*this);                     /* skipNeighborCell looks every member of every visited cell up */
     queueClear();                                  /* initPriorityQueue, mvs.cpp:90-95 */
     for (std::map<int, Patch>::const_iterator it = patches.begin(); it != patches.end(); ++it) queuePush(it->first);
     setNeighborRadius();
