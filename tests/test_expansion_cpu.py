@@ -82,12 +82,19 @@ def coverage(P, centers):
     return {(int(u / cs), int(v / cs)) for (u, v) in (P.o.cameras[0].project(list(c), 0, P.cfg.lodRatio)[0] for c in centers)}
 
 
-@pytest.mark.parametrize("strategy", [oh.BEST_FIRST, oh.WORST_FIRST, oh.BREATH_FIRST])
+@pytest.mark.parametrize("strategy", [oh.BEST_FIRST, oh.WORST_FIRST, oh.BREATH_FIRST, oh.DEPTH_FIRST])
 def test_round_of_one_is_the_serial_reference(hooks, cfg, strategy):
     P = seeded_pair(hooks, cfg, seed=31 + strategy, strategy=strategy)
     got, calls, refined = host_expand(P, 1, merge=False)
     want, want_refined = oracle_expand(P)
     assert len(want) > 300                                            # the plane was grown from six seeds
+    if strategy == oh.DEPTH_FIRST:
+        # the reference's backward scan never returns the first queued patch (mvs.cpp:761-788); the driver pops it last:
+        # everything up to there is the serial reference, plus at most that one patch's children
+        assert set(want) <= set(got) and len(got) - len(want) <= 4 * len(P.o.cameras)
+        assert want_refined <= refined <= want_refined + 4 * len(P.o.cameras)
+        P.close()
+        return
     assert sorted(got) == sorted(want)                                # same patches, bit for bit
     assert refined == want_refined                                    # and not one refinement more than the serial loop
     # the reference's own loop exit leaves the patch popped last unexpanded (mvs.cpp:241-243): at most its children differ
