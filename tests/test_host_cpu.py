@@ -141,3 +141,36 @@ def test_config_txt_parser(tmvs_bin, dataset, tmp_path):
     assert (c.adaptiveGradientEnable, c.adaptiveDistanceEnable, c.adaptiveDifferenceEnable) == (1, 0, want.adaptiveDifferenceEnable)
     assert (c.gradientWeighting, c.lodRatio, c.expansionStrategy, c.minRegionRatio, c.neighborRadiusScalar) == (0.125, 0.75, 2, 0.4, 0.02)
     assert (c.cellSize, c.minCamNum, c.maxCellPatchNum, c.distWeighting) == (want.cellSize, want.minCamNum, want.maxCellPatchNum, want.distWeighting)
+
+
+def test_nvm_seeds_match_the_oracle(tmvs_bin, dataset):
+    """NVM -> seeds as the reference builds them: camera line (fileloader.cpp:15-60), point line with measurements relative
+    to the INTEGER image centre (:112-165, `cols / 2`), seed ctor's estimated normal, then MVS::loadNVM's reCentering
+    (mvs.cpp:161-164, patch.cpp:67-112) — the host's result against oracle/orc_host.py's restatement, every seed."""
+    import orc_host as oh
+    d, path, cfg, sc = dataset
+    out = os.path.join(d, "seeds_oracle.mvs")
+    subprocess.check_call([tmvs_bin, "--convert", path, out, "--config", os.path.join(d, "config.txt")], cwd=d)
+    _, _, got = mvsio.read_mvs(out)
+    lines = [l for l in open(path).read().split("\n")]
+    assert lines[0] == "NVM_V3"
+    body = [l for l in lines[1:] if l.strip()]
+    ncam = int(body[0])
+    cams = []
+    for l in body[1:1 + ncam]:
+        t = l.split()
+        cams.append(oh.Camera(float(t[1]), [float(v) for v in t[2:6]], [float(v) for v in t[6:9]], sc.width, sc.height))
+    npt = int(body[1 + ncam])
+    o = oh.MVS(cfg, cams)
+    assert npt == len(got) == 24
+    for k, l in enumerate(body[2 + ncam:2 + ncam + npt]):
+        t = l.split()
+        n = int(t[6])
+        idx = [int(t[7 + 4 * i]) for i in range(n)]
+        pts = [(float(t[9 + 4 * i]) + sc.width // 2, float(t[10 + 4 * i]) + sc.height // 2) for i in range(n)]
+        p = oh.Patch(k, [float(v) for v in t[0:3]], [0.0, 0.0, 0.0], cam_idx=idx, img_point=pts)
+        oh.estimated_normal(o, p)                 # seed ctor, patch.cpp:26-34
+        oh.recentering(o, p)
+        assert got[k]["camIdx"] == idx
+        assert np.allclose(got[k]["center"], p.center, rtol=0, atol=1e-10)
+        assert np.allclose(got[k]["normalS"], p.normalS, rtol=0, atol=1e-10)
