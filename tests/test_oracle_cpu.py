@@ -213,3 +213,41 @@ def test_pyramid_restatement_against_cv2():
     gy = cv2.Sobel(img, cv2.CV_64F, 0, 1, ksize=1)
     m = np.sqrt(gx * gx + gy * gy)
     assert np.array_equal(e, (m - m.min()) / (m.max() - m.min()))
+
+
+def test_homographies_are_the_plane_induced_maps(small_scene):
+    """getHomographies (patch.cpp:290-330) pinned geometrically, independent of how it is computed: for points X on the
+    hypothesis plane, H_v maps the reference camera's pixel of X (at the patch's LOD) onto view v's pixel of X; the
+    reference view's H is the identity (:317-319). And the 3x3 inverse it uses (cv::Mat::inv, closed form for n <= 3)
+    against cv2.invert."""
+    cfg, sc = small_scene
+    o = orc.Oracle(cfg, sc.records, seed=42)
+    patches = sc.patches(6, seed=21)
+    rng = np.random.RandomState(4)
+    for lod in (0, 1, 2):
+        hyps = scene.hypotheses_from_patches(sc, patches, cfg, lod=lod, per_patch=2, spread=1.0)
+        for h in hyps:
+            Hs = np.array(o.homographies(h)).reshape(h.nCam, 3, 3)
+            ref = sc.cams[h.refCamIdx]
+            n = np.array([math.sin(h.theta) * math.cos(h.phi), math.sin(h.theta) * math.sin(h.phi), math.cos(h.theta)])
+            center = np.array(list(h.ray)) * h.depth + ref.center
+            a = np.cross(n, [1.0, 0.3, 0.2])
+            a /= np.linalg.norm(a)
+            b = np.cross(n, a)
+            for _ in range(5):
+                X = center + 0.2 * rng.randn() * a + 0.2 * rng.randn() * b          # on the plane
+                xr = ref.project(X, lod, cfg.lodRatio)
+                for k in range(h.nCam):
+                    v = h.camIdx[k]
+                    q = Hs[k] @ np.array([xr[0], xr[1], 1.0])
+                    assert np.allclose(q[:2] / q[2], sc.cams[v].project(X, lod, cfg.lodRatio), rtol=0, atol=1e-7)
+                    if v == h.refCamIdx:
+                        assert np.array_equal(Hs[k], np.eye(3))
+    cv2 = pytest.importorskip("cv2")
+    L = orc.lib()
+    for _ in range(50):
+        A = rng.randn(3, 3) * 10 ** rng.uniform(-2, 3)
+        out = (C.c_double * 9)()
+        L.orc_inv3(A.ravel().ctypes.data_as(C.POINTER(C.c_double)), out)
+        ok, ref_inv = cv2.invert(A)
+        assert ok != 0 and np.allclose(np.array(list(out)).reshape(3, 3), ref_inv, rtol=1e-12, atol=0)
