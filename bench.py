@@ -259,7 +259,7 @@ def run_gpu(args):
     pin_in = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
     pin_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
     e2e_t = []
-    for s in range(total_steps):
+    for s in range(0 if args.no_e2e else total_steps):
         pin_in.numpy()[:] = np.frombuffer(bytes(host_in[s]), dtype=np.uint8)
         if world > 1:
             dist.barrier()
@@ -274,7 +274,7 @@ def run_gpu(args):
     e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(e2e_total.item())
+    e2e_value = world * n * args.steps / float(e2e_total.item()) if e2e_t else None
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
@@ -326,6 +326,7 @@ def main():
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--cpu-patches", type=int, default=0, help="CPU sample size (0 = 128 per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the host-buffer end-to-end leg")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

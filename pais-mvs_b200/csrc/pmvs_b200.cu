@@ -43,15 +43,18 @@ __global__ void pack_quad_kernel(const uint8_t *__restrict__ grey, size_t pitch,
 
 /* carve the dynamic shared memory of one CTA */
 struct SmemPlan {
-    size_t ctaOff, viewOff, distOff, warpOff, corrOff, total;
+    size_t ctaOff, viewOff, distOff, warpOff, corrOff, refWinOff, total;
     size_t perWarp;      /* doubles per warp: H + xs + ys + column constants */
-    int vcap, ps, nWarps;
+    int vcap, ps, nWarps, slotViews, nRefWin;
 };
-static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t headBytes) {
+/* nRefWin: reference windows (RefWin tables) the CTA holds — one per CTA (refine), one per warp (fitness), 0 = none */
+static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t headBytes, bool useVL, int nRefWin) {
     SmemPlan pl;
     pl.vcap = vcap;
     pl.ps = ps;
     pl.nWarps = nWarps;
+    pl.slotViews = PMVS_SLOT_VIEWS_OF(vcap, useVL);
+    pl.nRefWin = nRefWin;
     size_t off = 0;
     pl.ctaOff = off;
     off += (headBytes + 15) & ~(size_t)15;
@@ -61,16 +64,19 @@ static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t he
     pl.distOff = off;
     off += sizeof(double) * ((size_t)PMVS_DIST_PAD(ps) + 64);     /* distance weights + exp table */
     pl.warpOff = off;
-    pl.perWarp = (((size_t)PMVS_HCAP(vcap) * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_HYP_DOUBLES + PMVS_COLV_DOUBLES(vcap, ps);
+    pl.perWarp = (((size_t)PMVS_HCAP(vcap) * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_HYP_DOUBLES + PMVS_COLV_DOUBLES_N(vcap, ps, pl.slotViews);
     off += sizeof(double) * pl.perWarp * nWarps;
     pl.corrOff = off;
     if (withCorr && !PMVS_CORR_GLOBAL(vcap)) off += sizeof(double) * (size_t)vcap * vcap;
+    off = (off + 15) & ~(size_t)15;
+    pl.refWinOff = off;
+    off += sizeof(double) * PMVS_REFWIN_DOUBLES(ps) * (size_t)nRefWin;
     pl.total = off;
     return pl;
 }
 struct SmemArgs {
-    unsigned ctaOff, viewOff, distOff, warpOff, corrOff, perWarp;
-    int vcap, ps;
+    unsigned ctaOff, viewOff, distOff, warpOff, corrOff, perWarp, refWinOff;
+    int vcap, ps, slotViews, nRefWin;
 };
 static SmemArgs to_args(const SmemPlan &pl) {
     SmemArgs a;
@@ -80,8 +86,11 @@ static SmemArgs to_args(const SmemPlan &pl) {
     a.warpOff = (unsigned)pl.warpOff;
     a.corrOff = (unsigned)pl.corrOff;
     a.perWarp = (unsigned)pl.perWarp;
+    a.refWinOff = (unsigned)pl.refWinOff;
     a.vcap = pl.vcap;
     a.ps = pl.ps;
+    a.slotViews = pl.slotViews;
+    a.nRefWin = pl.nRefWin;
     return a;
 }
 __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArgs &a, int warp) {
@@ -90,19 +99,21 @@ __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArg
     W.H = base;
     W.xs = base + (size_t)PMVS_HCAP(a.vcap) * 9;
     W.ys = W.xs + a.ps;
-    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES(a.vcap, a.ps);
+    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES_N(a.vcap, a.ps, a.slotViews);
     W.hyp = W.colv - PMVS_HYP_DOUBLES;
-    W.slotViews = PMVS_COLV_VIEWS(a.vcap);
+    W.slotViews = a.slotViews;
     W._padw = 0;
-    W.gv = W.colv + PMVS_COLV_SLOTS(a.vcap);
-    W.rowf = W.gv + PMVS_GV_DOUBLES_TOTAL(a.vcap);
+    W.gv = W.colv + PMVS_COLV_SLOTS_N(a.slotViews);
+    W.rowf = W.gv + PMVS_GV_DOUBLES_N(a.vcap, a.slotViews);
     W.rowi = (int2 *)(W.rowf + PMVS_PS_PAD(a.ps));
+    W.rw = nullptr;
     return W;
 }
 
 /* ---- seam 1 ------------------------------------------------------------------------------------------- */
 struct FitWarpS {
     EvalCtx E;
+    RefWin rw;
 };
 __global__ void __launch_bounds__(128) fitness_batch_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
                                                             const PmvsHypothesis *__restrict__ in, double *__restrict__ out) {
@@ -113,9 +124,14 @@ __global__ void __launch_bounds__(128) fitness_batch_kernel(const __grid_constan
     load_exp_table(sDistW, a.ps, tid, blockDim.x);
     /* one EvalCtx + view table per warp: ctaOff holds NW contexts, viewOff NW*vcap views */
     EvalCtx &E = ((FitWarpS *)(smem + a.ctaOff))[warp].E;
-    if (lane == 0) E.view = (ViewS *)(smem + a.viewOff) + (size_t)warp * a.vcap;
+    RefWin &R = ((FitWarpS *)(smem + a.ctaOff))[warp].rw;
+    if (lane == 0) {
+        E.view = (ViewS *)(smem + a.viewOff) + (size_t)warp * a.vcap;
+        if (a.nRefWin) carve_ref_win(R, (double *)(smem + a.refWinOff) + PMVS_REFWIN_DOUBLES(a.ps) * (size_t)warp, a.ps);
+    }
     __syncthreads();
-    const WarpWork W = warp_work(smem, a, warp);
+    WarpWork W = warp_work(smem, a, warp);
+    if (a.nRefWin) W.rw = &R;
     for (int h = blockIdx.x * NW + warp; h < n; h += gridDim.x * NW) {
         const PmvsHypothesis &hy = in[h];
         const double ray[3] = {hy.ray[0], hy.ray[1], hy.ray[2]};
@@ -124,6 +140,11 @@ __global__ void __launch_bounds__(128) fitness_batch_kernel(const __grid_constan
         __syncwarp();
         finish_eval_ctx(E, lane);
         __syncwarp();
+        if (a.nRefWin) {       /* every hypothesis is its own patch here: its reference window is built for it alone */
+            double ctr[3];
+            for (int k = 0; k < 3; ++k) ctr[k] = E.ray[k] * hy.depth + E.refC[k];
+            build_ref_win<true>(S, E, R, ctr, lane, 32);
+        }
         const double f = warp_fitness_any(S, E, sDistW, W, hy.theta, hy.phi, hy.depth);
         if (lane == 0) out[h] = f;
     }
@@ -208,8 +229,12 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
         c.E.view = (ViewS *)(smem + a.viewOff);
         c.part = (ParticleS *)(smem + a.ctaOff + ((sizeof(CtaS) + 15) & ~(size_t)15));
     }
-    const WarpWork W = warp_work(smem, a, warp);
+    WarpWork W = warp_work(smem, a, warp);
     const WarpWork W0 = warp_work(smem, a, 0);
+    if (a.nRefWin) {
+        if (tid == 0) carve_ref_win(c.rw, (double *)(smem + a.refWinOff), a.ps);
+        W.rw = &c.rw;
+    }
     __syncthreads();
     for (;;) {
         if (tid == 0) c.nextIdx = atomicAdd(counter, 1);
@@ -387,15 +412,32 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     ctx->cfg.patchSize = (cfg->patchRadius << 1) + 1;                               /* mvs.cpp:67 */
     const std::vector<double> w = dist_weight(ctx->cfg);
     if (ctx->dDistW) { cudaFree(ctx->dDistW); ctx->dDistW = nullptr; }
-    CK(cudaMalloc(&ctx->dDistW, w.size() * sizeof(double)));
-    CK(cudaMemcpy(ctx->dDistW, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+    /* the table, followed by its separable factor: w[x][y] = g[x] g[y] / (sum g)^2 (ones when the weight is disabled) */
+    std::vector<double> wg(w);
+    {
+        const int ps = ctx->cfg.patchSize, r = ctx->cfg.patchRadius;
+        const double s2 = 1.0 / (2.0 * ctx->cfg.distWeighting * ctx->cfg.distWeighting);
+        std::vector<double> g((size_t)ps, 1.0);
+        if (ctx->cfg.adaptiveDistanceEnable) {
+            double sum = 0;
+            for (int k = 0; k < ps; ++k) { g[k] = exp(-pow((double)(k - r), 2) * s2); sum += g[k]; }
+            for (int k = 0; k < ps; ++k) g[k] = g[k] / sum;
+        }
+        wg.insert(wg.end(), g.begin(), g.end());
+    }
+    CK(cudaMalloc(&ctx->dDistW, wg.size() * sizeof(double)));
+    CK(cudaMemcpy(ctx->dDistW, wg.data(), wg.size() * sizeof(double), cudaMemcpyHostToDevice));
     DevScene &s = ctx->scene;
     s.cfg = ctx->cfg;
     s.cams = ctx->dCams;
     s.distW = ctx->dDistW;
+    s.distG = ctx->dDistW + w.size();
     s.nCams = ctx->nCams;
     s.seed = ctx->seed;
-    s._pad = 0;
+    {
+        const char *envVL = getenv("PMVS_VL");          /* tuning / A-B: PMVS_VL=0 keeps the column-lane loop */
+        s.useVL = (envVL && atoi(envVL) == 0) ? 0 : 1;
+    }
     for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
     /* correlation scratch: one slab per resident CTA */
     const size_t stride = (size_t)ctx->vcap * ctx->cfg.patchSize * ctx->cfg.patchSize + (size_t)ctx->vcap * ctx->vcap + ctx->vcap;   /* windows + (global) correlation table + ratios */
@@ -655,11 +697,15 @@ int pmvs_fitness_batch(pmvs_ctx *ctx, int n, const PmvsHypothesis *in, double *o
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->dIn, in, sizeof(PmvsHypothesis) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     const int NW = 4;
-    SmemPlan pl = plan_smem(PMVS_MAX_VIEWS * NW, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW);
+    const bool useVL = ctx->scene.useVL != 0;
+    SmemPlan pl = plan_smem(PMVS_MAX_VIEWS * NW, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW, false, 0);
     /* the per-warp H area must hold PMVS_MAX_VIEWS homographies: plan with vcap = MAX_VIEWS for the warp area */
-    SmemPlan plw = plan_smem(PMVS_MAX_VIEWS, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW);
+    SmemPlan plw = plan_smem(PMVS_MAX_VIEWS, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW, false, 0);
     pl.perWarp = plw.perWarp;
-    pl.total = pl.warpOff + sizeof(double) * pl.perWarp * NW;
+    pl.slotViews = plw.slotViews;
+    pl.refWinOff = (pl.warpOff + sizeof(double) * pl.perWarp * NW + 15) & ~(size_t)15;
+    pl.nRefWin = useVL ? NW : 0;                                     /* one reference window per warp */
+    pl.total = pl.refWinOff + sizeof(double) * PMVS_REFWIN_DOUBLES(ctx->cfg.patchSize) * (size_t)pl.nRefWin;
     SmemArgs a = to_args(pl);
     a.vcap = PMVS_MAX_VIEWS;
     CK(cudaFuncSetAttribute(fitness_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
@@ -685,7 +731,9 @@ static int refine_config(pmvs_ctx *ctx, int NW, RefineCfg &c) {
     if (nPart > PMVS_MAX_PARTICLES) nPart = PMVS_MAX_PARTICLES;
     const size_t ctaBytes = ((sizeof(CtaS) + 15) & ~(size_t)15);
     c.NW = NW;
-    c.pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, ctaBytes + sizeof(ParticleS) * (size_t)nPart);
+    const bool useVL = ctx->scene.useVL != 0;
+    c.pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, ctaBytes + sizeof(ParticleS) * (size_t)nPart, useVL,
+                     (useVL && ctx->vcap >= 2 && ctx->vcap <= PMVS_VL_VIEWS) ? 1 : 0);
     /* three register budgets of the same kernel: 96 registers (20 warps/SM, NW <= 5), 128 (16 warps/SM, NW <= 8,
      * or one 16-warp CTA). Measured (8192 patches, P = 15): 3 views 217k vs 199k patches/s and 5 views 142k vs 137k in
      * favour of 96 registers, 8 views 54.8k vs 57.3k in favour of 128 (the wider view loops spill), 12 views equal. */

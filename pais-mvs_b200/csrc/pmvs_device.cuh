@@ -43,6 +43,12 @@
  * with the camera count are large already); every view count forms the x-parts inline there */
 #define PMVS_COLV_VIEWS(vcap) ((vcap) > 16 ? 0 : ((vcap) < 2 ? 1 : ((vcap) - 1 > PMVS_SLOT_VIEWS ? PMVS_SLOT_VIEWS : (vcap) - 1)))
 #define PMVS_CORR_GLOBAL(vcap) ((vcap) > 16)   /* the V x V correlation table (+ V region ratios) in the CTA's global scratch */
+/* scenes the view-lane loop covers (<= 9 cameras) keep no slots either: only its rare fallbacks reach the old loop */
+#define PMVS_VL_VIEWS 9
+#define PMVS_SLOT_VIEWS_OF(vcap, useVL) (((useVL) && (vcap) <= PMVS_VL_VIEWS) ? 0 : PMVS_COLV_VIEWS(vcap))
+#define PMVS_COLV_SLOTS_N(slotViews) (3 * (slotViews) * 32)
+#define PMVS_GV_DOUBLES_N(vcap, slotViews) (((slotViews) > 0 && (vcap) - 1 <= (slotViews)) ? 6 * ((vcap) < 2 ? 1 : (vcap) - 1) : 12 * ((vcap) < 2 ? 1 : (vcap) - 1))
+#define PMVS_COLV_DOUBLES_N(vcap, ps, slotViews) (PMVS_COLV_SLOTS_N(slotViews) + PMVS_GV_DOUBLES_N(vcap, slotViews) + 2 * PMVS_PS_PAD(ps))
 #define PMVS_COLV_SLOTS(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
 /* compact table of the non-reference views. Slot mode (<= PMVS_SLOT_VIEWS of them): 6 doubles each — h1, h4, h7, quad
  * pointer, cols, spare; inline mode: 12 — h0..h8, quad pointer, cols, spare */
@@ -68,9 +74,10 @@ struct DevScene {
     PmvsConfig cfg;
     const DevCamera *cams;
     const double *distW;       /* patchSize^2, index x*patchSize+y (mvs.cpp:104-109) */
+    const double *distG;       /* patchSize: distW[x][y] = distG[x] * distG[y] up to rounding (the Gaussian is separable) */
     double *scratch;           /* per-CTA correlation windows: scratchStride doubles per CTA */
     unsigned long long scratchStride;
-    int nCams, _pad;
+    int nCams, useVL;          /* useVL: the view-lane window loop (fitness_vl) is enabled */
     uint64_t seed;
     double lodScale[PMVS_MAX_LEVELS];
 };
@@ -89,6 +96,41 @@ struct EvalCtx {
     int refCols, refRows, refCam, LOD, V, valid;
     int refView, _pad;   /* index of the reference camera in view[] (-1: not among the views) */
 };
+/*
+ * Per-patch constants of the reference view (shared memory; built once per swarm run by build_ref_win).
+ * center = ray * depth + C_ref (patch.cpp:944) lies on the reference camera's viewing ray for every depth, so its
+ * reference-image position pt (patch.cpp:951), the window axes (:979-980), the reference view's samples (H = I,
+ * :317-319), the background-mask pixels (:986) and the distance weights (:1030-1032) are the same for every
+ * hypothesis of a swarm run up to the rounding of pt (~1e-13 pixel; hypotheses further than PMVS_PT_TOL from the
+ * canonical pt take the per-hypothesis path).
+ */
+#define PMVS_PT_TOL 1e-9
+#define PMVS_PS_PAD8(ps) (((ps) + 7) & ~7)          /* window rows incl. the padding rows of the view-lane loop's trips */
+#define PMVS_NYP(ps) (((PMVS_PS_PAD8(ps) + 11) & ~15) + 4)     /* row pitch of the colour table: = 4 (mod 16) doubles: conflict-free quads */
+struct RefWin {
+    double pt[2];
+    double *xs;                  /* nx sample columns (canonical window axes) */
+    double2 *ysg;                /* PAD8(ny) x {y, row factor of the separable distance weight}; padding rows repeat the last row */
+    double *gx;                  /* nx column factors of the distance weight */
+    unsigned long long *mask;    /* nx: bit (64/gl) (j % gl) + j / gl = reference pixel of (column, row j) is not background */
+    double *refc;                /* nx x nyp: the reference view's sample of every window position */
+    int nx, ny, nyp, ok, gl, _pad;
+};
+/* doubles one RefWin's tables take for patch size ps: xs | gx | ysg | mask | refc */
+#define PMVS_REFWIN_DOUBLES(ps) (5 * (size_t)PMVS_PS_PAD8(ps) + (size_t)(ps) * PMVS_NYP(ps))
+__device__ __forceinline__ void carve_ref_win(RefWin &R, double *base, int ps) {
+    const int pp = PMVS_PS_PAD8(ps);
+    R.xs = base;
+    R.gx = base + pp;
+    R.ysg = (double2 *)(base + 2 * pp);
+    R.mask = (unsigned long long *)(base + 4 * pp);
+    R.refc = base + 5 * pp;
+    R.nyp = PMVS_NYP(ps);
+    R.nx = R.ny = 0;
+    R.ok = 0;
+    R.gl = 4;
+}
+
 /* per-warp scratch (shared memory) */
 struct WarpWork {
     double *H;      /* V*9 */
@@ -100,6 +142,7 @@ struct WarpWork {
     double *gv;     /* PMVS_GV_DOUBLES_TOTAL(vcap): compact table of the non-reference views */
     double *rowf;   /* PMVS_PS_PAD(ps): fractional part of each window row in the reference view */
     int2 *rowi;     /* PMVS_PS_PAD(ps): {floor(y) * refCols, 2 * (cvRound(y) - floor(y))} per window row */
+    const RefWin *rw;   /* the patch's reference window (nullptr: none built) */
 };
 
 __device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -906,6 +949,340 @@ __device__ __noinline__ void fitness_columns_many(const DevScene &S, const EvalC
     swOut = warp_sum(sw);
 }
 
+__device__ __forceinline__ bool ref_window_ok(const DevScene &S, const EvalCtx &E, const double *center, double *pt);
+
+/* =====================================================================================================
+ * View-lane window loop (fitness_vl): the unchecked sample loop of getFitness (patch.cpp:979-1042) for 2..9 views
+ * over the patch's reference window (RefWin).
+ *
+ * A group of GL lanes owns one window column at a time (32/GL columns per pass) and GL consecutive rows of it.
+ * In the SAMPLE phase lane s of the group is a VIEW: it keeps the homography constants of non-reference view
+ * c*GL + s (c < NCH chunks) in registers — h1, h4, h7 and the x-parts A = h0 x + h2, B = h3 x + h5, C = h6 x + h8 of
+ * its current column — and samples that view at the group's GL rows, in the row order s^0, s^1, .. s^(GL-1). No
+ * shared-memory traffic for homographies, no per-lane slots. Then t = 1..GL-1 butterfly shuffles (lane s sends its
+ * sample of row s^t to lane s^t, a FIXED register: no selects) transpose the GL x GL block, and in the PIXEL phase
+ * lane s is a ROW: it holds the colours of all views at (column, row s), adds the reference view's colour from the
+ * RefWin table and does the cross-view mean / absolute deviations (patch.cpp:1019-1027), the difference weight
+ * (:1033-1035) and the accumulation (:1039-1040) for that one pixel. The views reach the lanes in the order
+ * s, s^1, s^2, s^3, i.e. as the unordered pairs {0,1}, {2,3}: the pairwise sums (c0 + c1) + (c2 + c3) are bit-identical
+ * on every lane because IEEE addition is commutative — results do not depend on the lane a pixel lands on.
+ * Per sample the arithmetic is column_coords / column_blend's (same expressions, same values). The distance weight
+ * is applied in its separable form gx[column] * gy[row] (RefWin), the background mask is one bit test.
+ * FULL: NG == GL * NCH (no padding views). Padding lanes sample view 0 again and their colours are discarded.
+ * =================================================================================================== */
+__device__ __forceinline__ double2 lds_f64x2(unsigned a) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(PMVS_FULL, v, m); }
+
+/* exp(x) of the difference weight for -700 <= x <= 0 as exp_table, with its constants in the constant bank (operands
+ * of the fma, no register or uniform-register traffic) */
+__constant__ double kExpT[8] = {92.33248261689366, -0.01083042469326756, -2.9815858269852933e-12, 8.33333333333333321769e-03,
+                                4.16666666666666643537e-02, 1.66666666666666657415e-01, 0.5, 1.0};
+__device__ __forceinline__ double exp_table_c(double x, unsigned tabA) {
+    const double t = fma(x, kExpT[0], 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, kExpT[1], x);
+    r = fma(kd, kExpT[2], r);
+    const double T = lds_f64(tabA + 8u * (unsigned)(k & 63));
+    double q = fma(r, kExpT[3], kExpT[4]);
+    q = fma(r, q, kExpT[5]);
+    q = fma(r, q, kExpT[6]);
+    q = fma(r, q, kExpT[7]);
+    const double p = fma(T * r, q, T);
+    return __hiloint2double(__double2hiint(p) + ((k >> 6) << 20), __double2loint(p));
+}
+
+/* N tap loads issued back to back: inside a (possibly divergent) device function every LDG needs the global-memory
+ * descriptor re-validated in a uniform register (LDC + 2 R2UR); adjacent loads share one */
+template <int N>
+__device__ __forceinline__ void ldg_group(const uint32_t *const *ad, uint32_t *q) {
+    if constexpr (N == 8) {
+        asm volatile("ld.global.nc.u32 %0, [%8];\n\tld.global.nc.u32 %1, [%9];\n\tld.global.nc.u32 %2, [%10];\n\tld.global.nc.u32 %3, [%11];\n\t"
+                     "ld.global.nc.u32 %4, [%12];\n\tld.global.nc.u32 %5, [%13];\n\tld.global.nc.u32 %6, [%14];\n\tld.global.nc.u32 %7, [%15];"
+                     : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+                     : "l"(ad[0]), "l"(ad[1]), "l"(ad[2]), "l"(ad[3]), "l"(ad[4]), "l"(ad[5]), "l"(ad[6]), "l"(ad[7]));
+    } else if constexpr (N == 4) {
+        asm volatile("ld.global.nc.u32 %0, [%4];\n\tld.global.nc.u32 %1, [%5];\n\tld.global.nc.u32 %2, [%6];\n\tld.global.nc.u32 %3, [%7];"
+                     : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3])
+                     : "l"(ad[0]), "l"(ad[1]), "l"(ad[2]), "l"(ad[3]));
+    } else {
+#pragma unroll
+        for (int n = 0; n < N; ++n) q[n] = __ldg(ad[n]);
+    }
+}
+
+/* N samples staged together (the stages of column_coords / column_blend): all projective coordinates, all reciprocals,
+ * all tap loads in flight before the first blend */
+template <int N>
+struct VlTaps {
+    double ix[N], fy[N];
+    uint32_t q[N];
+    int px[N];
+};
+
+#ifndef PMVS_VL_RB
+#define PMVS_VL_RB 2            /* row blocks (of GL rows) per trip of the view-lane loop */
+#endif
+
+template <int GL, int NCH, int RB, bool FULL>
+__device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *__restrict__ Hw,
+                                        const double *__restrict__ sExpT, double &fitOut, double &swOut) {
+    constexpr int CP = 32 / GL;                     /* columns per pass */
+    constexpr int LG = GL == 4 ? 2 : (GL == 2 ? 1 : 0);
+    constexpr int NS = NCH * GL * RB;               /* samples of one lane per trip */
+    constexpr int FW = 64 / GL;                     /* width of one lane's field of the row mask */
+    const int lane = threadIdx.x & 31, s = lane & (GL - 1), ci = lane >> LG;
+    const int V = E.V, NG = V - 1, refV = E.refView, nx = R.nx, nyp = R.nyp;
+    const int ny = (R.ny + GL * RB - 1) / (GL * RB) * (GL * RB);       /* rows incl. padding (padding rows carry mask bit 0) */
+    const unsigned hA = smem_addr(Hw), xsA = smem_addr(R.xs), gxA = smem_addr(R.gx), ysgA = smem_addr(R.ysg), mkA = smem_addr(R.mask);
+    const unsigned rcA = smem_addr(R.refc), tabA = smem_addr(sExpT), viewA = smem_addr(E.view);
+    const double invV = 1.0 / (double)V;
+    const double negK = S.cfg.adaptiveDifferenceEnable ? -(invV * invV) / S.cfg.diffWeighting : 0.0;
+
+    /* this lane's views */
+    double h1[NCH], h4[NCH], h7[NCH];
+    const uint32_t *quad[NCH];
+    int cols[NCH];
+    unsigned hv[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        int k = c * GL + s;
+        if (!FULL && k >= NG) k = 0;
+        const int v = k + (k >= refV ? 1 : 0);
+        hv[c] = hA + 72u * (unsigned)v;
+        h1[c] = lds_f64(hv[c] + 8u);
+        h4[c] = lds_f64(hv[c] + 32u);
+        h7[c] = lds_f64(hv[c] + 56u);
+        const unsigned va = viewA + (unsigned)(sizeof(ViewS) * v);
+        quad[c] = (const uint32_t *)lds_u64(va + (unsigned)offsetof(ViewS, quad));
+        cols[c] = lds_s32(va + (unsigned)offsetof(ViewS, cols));
+    }
+    /* which of the views that reach this lane in the pixel phase are real (padding views excluded) */
+    bool real[NCH][GL];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int t = 0; t < GL; ++t) real[c][t] = FULL || (c * GL + (s ^ t)) < NG;
+    /* row addresses of the sample phase: rows (s ^ t) of the current block; of the pixel phase: row s */
+    unsigned ya[GL];
+#pragma unroll
+    for (int t = 0; t < GL; ++t) ya[t] = ysgA + 16u * (unsigned)(s ^ t);
+
+    double fit = 0, sw = 0;
+    for (int i0 = 0; i0 < nx; i0 += CP) {
+        const int i = i0 + ci;
+        const bool colOk = i < nx;
+        const int ic = colOk ? i : nx - 1;
+        const double x = lds_f64(xsA + 8u * ic);
+        const double gxv = colOk ? lds_f64(gxA + 8u * ic) : 0.0;
+        const unsigned long long mk = lds_u64(mkA + 8u * ic) >> (FW * s);     /* bit b = row GL * b + s of this column */
+        unsigned mlo = (unsigned)mk, mhi = (unsigned)(mk >> 32);
+        double A[NCH], B[NCH], C[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            A[c] = fma(lds_f64(hv[c]), x, lds_f64(hv[c] + 16u));
+            B[c] = fma(lds_f64(hv[c] + 24u), x, lds_f64(hv[c] + 40u));
+            C[c] = fma(lds_f64(hv[c] + 48u), x, lds_f64(hv[c] + 64u));
+        }
+        unsigned rcol = rcA + 8u * (unsigned)(ic * nyp + s);
+        double cfit = 0, csw = 0;
+        for (int jo = 0; jo < 16 * ny; jo += 16 * GL * RB) {       /* jo: byte offset of the block's first row in ysg */
+            /* ---- sample phase: my views at rows (s ^ t) of each block ---- */
+            VlTaps<NS> tp;
+            {
+                double w[NS], r[NS], e[NS], y[RB * GL];
+#pragma unroll
+                for (int b = 0; b < RB; ++b)
+#pragma unroll
+                    for (int t = 0; t < GL; ++t) y[b * GL + t] = lds_f64(ya[t] + (unsigned)jo + 16u * GL * b);
+#pragma unroll
+                for (int n = 0; n < NS; ++n) w[n] = fma(h7[n / (GL * RB)], y[n % (GL * RB)], C[n / (GL * RB)]);
+#pragma unroll
+                for (int n = 0; n < NS; ++n) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(w[n]));
+#pragma unroll
+                for (int n = 0; n < NS; ++n) e[n] = fma(-w[n], r[n], 1.0);
+#pragma unroll
+                for (int n = 0; n < NS; ++n) e[n] = fma(e[n], e[n], e[n]);
+#pragma unroll
+                for (int n = 0; n < NS; ++n) r[n] = fma(r[n], e[n], r[n]);
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    tp.ix[n] = fma(h1[n / (GL * RB)], y[n % (GL * RB)], A[n / (GL * RB)]) * r[n];
+                    tp.fy[n] = fma(h4[n / (GL * RB)], y[n % (GL * RB)], B[n / (GL * RB)]) * r[n];       /* iy */
+                }
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    w[n] = __dadd_rd(tp.ix[n], PMVS_MAGIC_FLOOR);
+                    r[n] = __dadd_rd(tp.fy[n], PMVS_MAGIC_FLOOR);
+                }
+                const uint32_t *ad[NS];
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    tp.px[n] = __double2loint(w[n]);
+                    ad[n] = quad[n / (GL * RB)] + (__double2loint(r[n]) * cols[n / (GL * RB)] + tp.px[n]);
+                }
+                ldg_group<NS>(ad, tp.q);
+#pragma unroll
+                for (int n = 0; n < NS; ++n) tp.fy[n] = tp.fy[n] - (r[n] - PMVS_MAGIC_FLOOR);
+            }
+            /* the pixel phase's own loads: reference colour and row weight of row GL*b + s */
+            double cref[RB], gy[RB];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                cref[b] = lds_f64(rcol + 8u * GL * b);
+                gy[b] = lds_f64(ya[0] + (unsigned)jo + 16u * GL * b + 8u);
+            }
+            rcol += 8u * GL * RB;
+            /* ---- blend (column_blend) ---- */
+            double col[NS];
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+                const int g00 = (int)__byte_perm(tp.q[n], 0, 0x4440), g01 = (int)__byte_perm(tp.q[n], 0, 0x4441);
+                const int g10 = (int)__byte_perm(tp.q[n], 0, 0x4442), g11 = (int)__byte_perm(tp.q[n], 0, 0x4443);
+                const int ndx = g00 - g01, idy = g10 - g00, ndxy = g10 - g11 - ndx;
+                const int k0 = tp.px[n] * ndx + g00, k1 = tp.px[n] * ndxy + idy;
+                col[n] = fma(tp.fy[n], fma(-tp.ix[n], cvt_a(ndxy), cvt_b(k1)), fma(-tp.ix[n], cvt_a(ndx), cvt_b(k0)));
+            }
+            /* ---- transpose: afterwards col[(c, b, t)] = view c*GL + (s ^ t) at row GL*b + s of the trip ---- */
+#pragma unroll
+            for (int n = 0; n < NS; ++n)
+                if (n % GL) col[n] = shfl_xor_f64(col[n], n % GL);
+            /* ---- pixel phase ---- */
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                double cv[NCH][GL];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int t = 0; t < GL; ++t) cv[c][t] = (FULL || real[c][t]) ? col[(c * RB + b) * GL + t] : 0.0;
+                double sum = tree_sum<GL>(cv[0]);
+#pragma unroll
+                for (int c = 1; c < NCH; ++c) sum += tree_sum<GL>(cv[c]);
+                sum += cref[b];
+                const double mean = sum * invV;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int t = 0; t < GL; ++t) cv[c][t] = (FULL || real[c][t]) ? fabs(cv[c][t] - mean) : 0.0;
+                double dev = tree_sum<GL>(cv[0]);
+#pragma unroll
+                for (int c = 1; c < NCH; ++c) dev += tree_sum<GL>(cv[c]);
+                dev += fabs(cref[b] - mean);
+                const double wgt = gy[b] * exp_table_c(dev * dev * negK, tabA);                  /* patch.cpp:1030-1035 */
+                if (mlo & (1u << b)) {                                                         /* patch.cpp:986 */
+                    csw += wgt;
+                    cfit = fma(wgt, dev, cfit);
+                }
+            }
+            if (GL == 1) mlo = __funnelshift_r(mlo, mhi, RB), mhi >>= RB;
+            else mlo >>= RB;
+        }
+        sw = fma(gxv, csw, sw);
+        fit = fma(gxv, cfit, fit);
+    }
+    fitOut = warp_sum(fit) * invV;
+    swOut = warp_sum(sw);
+}
+
+/* dispatch on the number of non-reference views NG = 1..8; false: not covered */
+__device__ __forceinline__ bool fitness_vl_dispatch(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *Hw, const double *sExpT,
+                                                    double &fit, double &sw) {
+    switch (E.V - 1) {
+    case 1: fitness_vl<1, 1, 8, true>(S, E, R, Hw, sExpT, fit, sw); return true;
+    case 2: fitness_vl<2, 1, 4, true>(S, E, R, Hw, sExpT, fit, sw); return true;
+    case 3: fitness_vl<4, 1, PMVS_VL_RB, false>(S, E, R, Hw, sExpT, fit, sw); return true;
+    case 4: fitness_vl<4, 1, PMVS_VL_RB, true>(S, E, R, Hw, sExpT, fit, sw); return true;
+    case 5: case 6: case 7: fitness_vl<4, 2, 1, false>(S, E, R, Hw, sExpT, fit, sw); return true;
+    case 8: fitness_vl<4, 2, 1, true>(S, E, R, Hw, sExpT, fit, sw); return true;
+    default: return false;
+    }
+}
+/* configurations the view-lane loop covers: no gradient weight (it would need a per-pixel table of the reference edge
+ * term), difference-weight exponent provably in [-700, 0] (|deviation| <= 255 per view) */
+__device__ __forceinline__ bool vl_config_ok(const DevScene &S) {
+    return S.useVL && !S.cfg.adaptiveGradientEnable &&
+           (!S.cfg.adaptiveDifferenceEnable || -(255.0 * 255.0) / S.cfg.diffWeighting >= -700.0);
+}
+
+/*
+ * Build the patch's reference window for the hypothesis centre `center` (any point of the viewing ray). Collective over
+ * `nthreads` threads with index tid (a whole CTA: WARP = false, barriers are __syncthreads; one warp: WARP = true).
+ * R.ok = 0 when the fast path cannot be used for this swarm run (window test of patch.cpp:951-962 fails at the canonical
+ * point, window sample count differs from patchSize^2, reference camera not among the views).
+ */
+template <bool WARP>
+__device__ __forceinline__ void ref_win_sync() {
+    if (WARP) __syncwarp();
+    else __syncthreads();
+}
+template <bool WARP>
+__device__ __forceinline__ void build_ref_win(const DevScene &S, const EvalCtx &E, RefWin &R, const double *center, int tid, int nthreads) {
+    const int radius = S.cfg.patchRadius, ps = S.cfg.patchSize;
+    if (tid == 0) {
+        R.ok = 0;
+        R.nx = R.ny = 0;
+        if (E.valid && E.refView >= 0 && E.V >= 2 && E.V <= 9 && vl_config_ok(S)) {
+            double pt[2];
+            const double c[3] = {center[0], center[1], center[2]};
+            if (ref_window_ok(S, E, c, pt)) {
+                R.pt[0] = pt[0];
+                R.pt[1] = pt[1];
+                R.ok = 1;
+            }
+        }
+    }
+    ref_win_sync<WARP>();
+    if (!R.ok) return;                                   /* uniform */
+    if (tid < 32) {
+        /* axes: xs directly, ys through the gx area (filled with the weights afterwards) */
+        const double pt[2] = {R.pt[0], R.pt[1]};
+        const int nxy = warp_window_axes(pt, radius, ps, R.xs, R.gx);
+        const int nx = nxy & 0xffff, ny = nxy >> 16;
+        if (nx == ps && ny == ps) {
+            for (int j = tid; j < PMVS_PS_PAD8(ps); j += 32)
+                R.ysg[j] = j < ny ? make_double2(R.gx[j], __ldg(S.distG + j)) : make_double2(R.gx[ny - 1], 0.0);
+            __syncwarp();
+            for (int i = tid; i < nx; i += 32) {
+                R.gx[i] = __ldg(S.distG + i);
+                R.mask[i] = 0ull;
+            }
+        }
+        if (tid == 0) {
+            R.nx = nx;
+            R.ny = ny;
+            R.gl = E.V == 2 ? 1 : (E.V == 3 ? 2 : 4);
+            if (nx != ps || ny != ps) R.ok = 0;          /* a rounding step of the ++x recurrence dropped a sample: rare, slow path */
+        }
+    }
+    ref_win_sync<WARP>();
+    if (!R.ok) return;
+    const int nx = R.nx, ny = R.ny, nyPad = PMVS_PS_PAD8(ps), refCols = E.refCols, gl = R.gl, fw = 64 / gl;
+    const uint32_t *__restrict__ refQuad = E.refQuad;
+    for (int idx = tid; idx < nx * nyPad; idx += nthreads) {
+        const int i = idx / nyPad, j = idx - i * nyPad;
+        if (j >= ny) {
+            R.refc[i * R.nyp + j] = 0.0;
+            continue;
+        }
+        const double x = R.xs[i], y = R.ysg[j].x;
+        const double tx = __dadd_rd(x, PMVS_MAGIC_FLOOR), ty = __dadd_rd(y, PMVS_MAGIC_FLOOR);
+        const int px = __double2loint(tx), py = __double2loint(ty);
+        RefColumn rc;
+        rc.quad = refQuad + px;
+        rc.fx = x - (tx - PMVS_MAGIC_FLOOR);
+        rc.selx = __double2int_rn(x) - px;
+        bool keep;
+        const double c = ref_sample(rc, make_int2(py * refCols, 2 * (__double2int_rn(y) - py)), y - (ty - PMVS_MAGIC_FLOOR), keep);
+        R.refc[i * R.nyp + j] = c;
+        if (keep) atomicOr(R.mask + i, 1ull << (fw * (j & (gl - 1)) + j / gl));
+    }
+    ref_win_sync<WARP>();
+}
+
 template <int V>
 __device__ __forceinline__ bool fitness_columns_dispatch(int nV, const DevScene &S, const EvalCtx &E, const double *sDistW,
                                                          const double *sExpT, const WarpWork &W, int nx, int ny, double &fit,
@@ -994,7 +1371,38 @@ __device__ __noinline__ double warp_window(const DevScene &S, const EvalCtx &E, 
     if (!ok) return DBL_MAX;                                                          /* :999-1002 */
     return fit / sw;                                                                  /* :1046 */
 }
+/* the view-lane route: the hypothesis sits on the patch's reference window and all four window corners project inside
+ * every view (same test as warp_window). Returns false when the hypothesis has to take the per-hypothesis path. */
+__device__ __noinline__ bool warp_window_vl(const DevScene &S, const EvalCtx &E, const double *sExpT, const WarpWork &W, const double *pt,
+                                            double &result) {
+    const RefWin &R = *W.rw;
+    if (!(fabs(pt[0] - R.pt[0]) <= PMVS_PT_TOL && fabs(pt[1] - R.pt[1]) <= PMVS_PT_TOL)) return false;
+    const int lane = threadIdx.x & 31;
+    const int nx = R.nx, ny = R.ny;
+    bool inside = true;
+    for (int t = lane; t < 4 * E.V; t += 32) {
+        const int v = t >> 2, cidx = t & 3;
+        const double *H = W.H + 9 * v;
+        const ViewS &vw = E.view[v];
+        const double loX = 2.0 + PMVS_EDGE_EPS, hiX = (double)(vw.cols - 3) - PMVS_EDGE_EPS;
+        const double loY = 2.0 + PMVS_EDGE_EPS, hiY = (double)(vw.rows - 3) - PMVS_EDGE_EPS;
+        const double x = R.xs[(cidx & 1) ? nx - 1 : 0], y = R.ysg[(cidx & 2) ? ny - 1 : 0].x;
+        const double w = H[6] * x + H[7] * y + H[8];
+        const double nxw = H[0] * x + H[1] * y + H[2], nyw = H[3] * x + H[4] * y + H[5];
+        if (!(w > 0.0 && nxw >= loX * w && nxw < hiX * w && nyw >= loY * w && nyw < hiY * w)) inside = false;
+    }
+    if (!__all_sync(PMVS_FULL, inside)) return false;
+    double fit, sw;
+    if (!fitness_vl_dispatch(S, E, R, W.H, sExpT, fit, sw)) return false;
+    __syncwarp();
+    result = fit / sw;                                                                /* patch.cpp:1046 */
+    return true;
+}
 __device__ __forceinline__ double warp_window_any(const DevScene &S, const EvalCtx &E, const double *sDistW, const WarpWork &W, const double *pt) {
+    if (W.rw && W.rw->ok) {
+        double f;
+        if (warp_window_vl(S, E, sDistW + PMVS_DIST_PAD(S.cfg.patchSize), W, pt, f)) return f;
+    }
     if (E.V <= 8) return warp_window<8>(S, E, sDistW, W, pt);
     if (E.V <= 16) return warp_window<16>(S, E, sDistW, W, pt);
     return warp_window<0>(S, E, sDistW, W, pt);

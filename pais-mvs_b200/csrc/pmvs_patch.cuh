@@ -36,6 +36,7 @@ struct CtaS {
     ParticleS *part;                    /* 2*particleNum entries (seeds run 2P particles, patch.cpp:192) */
     MoveS mv;
     PmvsPatchOut out;
+    RefWin rw;                          /* reference window of the current swarm run (tables carved by the kernel) */
     int nextIdx;
 };
 
@@ -380,6 +381,11 @@ __device__ inline void cta_pso_optimization(const DevScene &S, CtaS &c, const do
     PatchS &p = c.p;
     const int tid = threadIdx.x;
     cta_build_ctx(S, c);
+    if (W.rw) {                                           /* uniform: the launch either carries reference windows or not */
+        /* canonical hypothesis centre = the initial particle's (patch.cpp:204, :944) */
+        const double ctr[3] = {c.E.ray[0] * p.depth + c.E.refC[0], c.E.ray[1] * p.depth + c.E.refC[1], c.E.ray[2] * p.depth + c.E.refC[2]};
+        build_ref_win<false>(S, c.E, c.rw, ctr, tid, blockDim.x);
+    }
     __shared__ double sInit[3];
     if (tid == 0) {
         const double PI = 3.14159265358979323846;
