@@ -86,10 +86,14 @@ void initDistWeight(Scene &s) {
             double e = -(pow((double)(x - r), 2) + pow((double)(y - r), 2)) * s2;
             s.distW[(size_t)x * ps + y] = sc * exp(e);
         }
-    /* cv::sum accumulates row by row in index order */
+    /* cv::sum on CV_64F (OpenCV 2.4 stat.cpp sum_): s0 += src[i] + src[i+1] + src[i+2] + src[i+3] four at a time over the
+     * continuous matrix, remainder one by one; `Mat / n` is a multiplication by 1./n (matop.cpp operator/(Mat,double)) */
     double n = 0;
-    for (size_t i = 0; i < s.distW.size(); ++i) n += s.distW[i];
-    for (size_t i = 0; i < s.distW.size(); ++i) s.distW[i] = s.distW[i] / n;
+    size_t i = 0;
+    for (; i + 4 <= s.distW.size(); i += 4) n += s.distW[i] + s.distW[i + 1] + s.distW[i + 2] + s.distW[i + 3];
+    for (; i < s.distW.size(); ++i) n += s.distW[i];
+    const double rn = 1. / n;
+    for (i = 0; i < s.distW.size(); ++i) s.distW[i] = s.distW[i] * rn;
 }
 
 void applyConfig(Scene &s, const PmvsConfig &cfg) {
@@ -734,8 +738,8 @@ bool getHomographyPatch(const Scene &s, const double pt[2], const Level &img, co
             sum += v * v;
             ++count;
         }
-    double n = sqrt(sum);
-    for (size_t i = 0; i < hp.size(); ++i) hp[i] /= n;
+    const double rn = 1. / sqrt(sum);                    /* hp /= sqrt(sum): Mat /= s is convertTo(.., 1./s) (OpenCV 2.4 mat.hpp) */
+    for (size_t i = 0; i < hp.size(); ++i) hp[i] = hp[i] * rn;
     return true;
 }
 

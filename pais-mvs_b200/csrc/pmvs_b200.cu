@@ -213,10 +213,32 @@ __device__ inline void patch_to_out(const PatchS &p, PmvsPatchOut &o) {
     }
 }
 
+/*
+ * Work distribution of the persistent CTAs. The batch is cut into nChunks contiguous index ranges, one per SM; the
+ * CTAs resident on an SM pull consecutive indices from their SM's range, so the patches an SM works on at the same time
+ * are neighbours in batch order. Callers hand candidates over in spatial order (grid scan / sorted by reference cell),
+ * so neighbouring patches share most of their image footprint and the SM's L1 holds one footprint instead of one
+ * per CTA. A CTA whose home range is exhausted steals from the following ranges; counters: counter[0..nChunks).
+ * nChunks = 1 is the plain shared counter.
+ */
+#define PMVS_MAX_CHUNKS 1024
+__device__ __forceinline__ int next_patch(int *counter, int n, int nChunks, int home) {
+    for (int t = 0; t < nChunks; ++t) {
+        int k = home + t;
+        if (k >= nChunks) k -= nChunks;
+        const int lo = (int)((long long)n * k / nChunks), len = (int)((long long)n * (k + 1) / nChunks) - lo;
+        if (len > 0 && *(volatile int *)(counter + k) < len) {
+            const int i = atomicAdd(counter + k, 1);
+            if (i < len) return lo + i;
+        }
+    }
+    return n;
+}
+
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constant__ DevScene S, const SmemArgs a, int n,
                                                         const PmvsPatchIn *__restrict__ in, PmvsPatchOut *__restrict__ out,
-                                                        uint32_t flags, int *__restrict__ counter) {
+                                                        uint32_t flags, int *__restrict__ counter, int nChunks) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     CtaS &c = *(CtaS *)(smem + a.ctaOff);
@@ -235,9 +257,15 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
         if (tid == 0) carve_ref_win(c.rw, (double *)(smem + a.refWinOff), a.ps);
         W.rw = &c.rw;
     }
+    int home = 0;
+    if (nChunks > 1) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        home = (int)(smid % (unsigned)nChunks);
+    }
     __syncthreads();
     for (;;) {
-        if (tid == 0) c.nextIdx = atomicAdd(counter, 1);
+        if (tid == 0) c.nextIdx = next_patch(counter, n, nChunks, home);
         __syncthreads();
         const int idx = c.nextIdx;
         if (idx >= n) break;
@@ -389,9 +417,13 @@ static std::vector<double> dist_weight(const PmvsConfig &cfg) {
             const double e = -(pow((double)(x - r), 2) + pow((double)(y - r), 2)) * s2;
             w[(size_t)x * ps + y] = s * exp(e);
         }
+    /* cv::sum on CV_64F adds four elements at a time; `Mat / n` multiplies by 1./n (OpenCV 2.4 stat.cpp, matop.cpp) */
     double n = 0;
-    for (size_t i = 0; i < w.size(); ++i) n += w[i];
-    for (size_t i = 0; i < w.size(); ++i) w[i] = w[i] / n;
+    size_t i = 0;
+    for (; i + 4 <= w.size(); i += 4) n += w[i] + w[i + 1] + w[i + 2] + w[i + 3];
+    for (; i < w.size(); ++i) n += w[i];
+    const double rn = 1. / n;
+    for (i = 0; i < w.size(); ++i) w[i] = w[i] * rn;
     return w;
 }
 
@@ -568,7 +600,7 @@ static int create_impl(pmvs_ctx *ctx, const PmvsConfig *cfg, int nCams, const Pm
     ctx->nCams = nCams;
     ctx->vcap = nCams < PMVS_MAX_VIEWS ? nCams : PMVS_MAX_VIEWS;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&ctx->dCounter, sizeof(int)));
+    CK(cudaMalloc(&ctx->dCounter, sizeof(int) * PMVS_MAX_CHUNKS));
 
     std::vector<DevCamera> hc(nCams);
     for (int i = 0; i < nCams; ++i) {
@@ -720,7 +752,7 @@ int pmvs_fitness_batch(pmvs_ctx *ctx, int n, const PmvsHypothesis *in, double *o
 }
 
 /* one launch configuration of refine_kernel: NW warps per CTA on one of the register budgets */
-typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *);
+typedef void (*RefineFn)(const DevScene, const SmemArgs, int, const PmvsPatchIn *, PmvsPatchOut *, uint32_t, int *, int);
 struct RefineCfg {
     int NW, perSm;
     RefineFn fn;
@@ -819,8 +851,12 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    CK(cudaMemsetAsync(ctx->dCounter, 0, sizeof(int), st));
-    fn<<<grid, NW * 32, pl.total, st>>>(ctx->scene, to_args(pl), n, d_in, d_out, flags, ctx->dCounter);
+    /* one index range per SM when the batch gives every SM a few patches per CTA slot; else one shared counter */
+    int nChunks = ctx->smCount < PMVS_MAX_CHUNKS ? ctx->smCount : PMVS_MAX_CHUNKS;
+    if (n < 4 * grid) nChunks = 1;
+    if (const char *envL = getenv("PMVS_LOCAL")) { if (atoi(envL) == 0) nChunks = 1; }      /* tuning / A-B */
+    CK(cudaMemsetAsync(ctx->dCounter, 0, sizeof(int) * PMVS_MAX_CHUNKS, st));
+    fn<<<grid, NW * 32, pl.total, st>>>(ctx->scene, to_args(pl), n, d_in, d_out, flags, ctx->dCounter, nChunks);
     ctx->launches++;
     CK(cudaGetLastError());
     return PMVS_OK;

@@ -1027,6 +1027,9 @@ struct VlTaps {
 #ifndef PMVS_VL_RB
 #define PMVS_VL_RB 2            /* row blocks (of GL rows) per trip of the view-lane loop */
 #endif
+#ifndef PMVS_VL_PIPE
+#define PMVS_VL_PIPE 1          /* 1: software-pipelined trips (tap loads of trip t+1 issued before the pixel phase of trip t) */
+#endif
 
 template <int GL, int NCH, int RB, bool FULL>
 __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *__restrict__ Hw,
@@ -1035,9 +1038,11 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
     constexpr int LG = GL == 4 ? 2 : (GL == 2 ? 1 : 0);
     constexpr int NS = NCH * GL * RB;               /* samples of one lane per trip */
     constexpr int FW = 64 / GL;                     /* width of one lane's field of the row mask */
+    constexpr unsigned STEP = 16u * GL * RB;        /* bytes of ysg one trip covers */
     const int lane = threadIdx.x & 31, s = lane & (GL - 1), ci = lane >> LG;
     const int V = E.V, NG = V - 1, refV = E.refView, nx = R.nx, nyp = R.nyp;
     const int ny = (R.ny + GL * RB - 1) / (GL * RB) * (GL * RB);       /* rows incl. padding (padding rows carry mask bit 0) */
+    const unsigned END = 16u * (unsigned)ny;
     const unsigned hA = smem_addr(Hw), xsA = smem_addr(R.xs), gxA = smem_addr(R.gx), ysgA = smem_addr(R.ysg), mkA = smem_addr(R.mask);
     const unsigned rcA = smem_addr(R.refc), tabA = smem_addr(sExpT), viewA = smem_addr(E.view);
     const double invV = 1.0 / (double)V;
@@ -1072,118 +1077,170 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
 #pragma unroll
     for (int t = 0; t < GL; ++t) ya[t] = ysgA + 16u * (unsigned)(s ^ t);
 
-    double fit = 0, sw = 0;
-    for (int i0 = 0; i0 < nx; i0 += CP) {
+    /* ---- the phases of one trip ---- */
+    double A[NCH], B[NCH], C[NCH];
+    /* x-parts of this lane's views for column pass i0 (sample side) */
+    auto sample_column = [&](int i0) {
         const int i = i0 + ci;
-        const bool colOk = i < nx;
-        const int ic = colOk ? i : nx - 1;
+        const int ic = i < nx ? i : nx - 1;
         const double x = lds_f64(xsA + 8u * ic);
-        const double gxv = colOk ? lds_f64(gxA + 8u * ic) : 0.0;
-        const unsigned long long mk = lds_u64(mkA + 8u * ic) >> (FW * s);     /* bit b = row GL * b + s of this column */
-        unsigned mlo = (unsigned)mk, mhi = (unsigned)(mk >> 32);
-        double A[NCH], B[NCH], C[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             A[c] = fma(lds_f64(hv[c]), x, lds_f64(hv[c] + 16u));
             B[c] = fma(lds_f64(hv[c] + 24u), x, lds_f64(hv[c] + 40u));
             C[c] = fma(lds_f64(hv[c] + 48u), x, lds_f64(hv[c] + 64u));
         }
-        unsigned rcol = rcA + 8u * (unsigned)(ic * nyp + s);
-        double cfit = 0, csw = 0;
-        for (int jo = 0; jo < 16 * ny; jo += 16 * GL * RB) {       /* jo: byte offset of the block's first row in ysg */
-            /* ---- sample phase: my views at rows (s ^ t) of each block ---- */
-            VlTaps<NS> tp;
-            {
-                double w[NS], r[NS], e[NS], y[RB * GL];
+    };
+    /* sample phase: my views at rows (s ^ t) of each block of the trip at byte offset jo; tap loads issued */
+    auto sample = [&](unsigned jo, VlTaps<NS> &tp) {
+        double w[NS], r[NS], e[NS], y[RB * GL];
 #pragma unroll
-                for (int b = 0; b < RB; ++b)
+        for (int b = 0; b < RB; ++b)
 #pragma unroll
-                    for (int t = 0; t < GL; ++t) y[b * GL + t] = lds_f64(ya[t] + (unsigned)jo + 16u * GL * b);
+            for (int t = 0; t < GL; ++t) y[b * GL + t] = lds_f64(ya[t] + jo + 16u * GL * b);
 #pragma unroll
-                for (int n = 0; n < NS; ++n) w[n] = fma(h7[n / (GL * RB)], y[n % (GL * RB)], C[n / (GL * RB)]);
+        for (int n = 0; n < NS; ++n) w[n] = fma(h7[n / (GL * RB)], y[n % (GL * RB)], C[n / (GL * RB)]);
 #pragma unroll
-                for (int n = 0; n < NS; ++n) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(w[n]));
+        for (int n = 0; n < NS; ++n) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(w[n]));
 #pragma unroll
-                for (int n = 0; n < NS; ++n) e[n] = fma(-w[n], r[n], 1.0);
+        for (int n = 0; n < NS; ++n) e[n] = fma(-w[n], r[n], 1.0);
 #pragma unroll
-                for (int n = 0; n < NS; ++n) e[n] = fma(e[n], e[n], e[n]);
+        for (int n = 0; n < NS; ++n) e[n] = fma(e[n], e[n], e[n]);
 #pragma unroll
-                for (int n = 0; n < NS; ++n) r[n] = fma(r[n], e[n], r[n]);
+        for (int n = 0; n < NS; ++n) r[n] = fma(r[n], e[n], r[n]);
 #pragma unroll
-                for (int n = 0; n < NS; ++n) {
-                    tp.ix[n] = fma(h1[n / (GL * RB)], y[n % (GL * RB)], A[n / (GL * RB)]) * r[n];
-                    tp.fy[n] = fma(h4[n / (GL * RB)], y[n % (GL * RB)], B[n / (GL * RB)]) * r[n];       /* iy */
-                }
-#pragma unroll
-                for (int n = 0; n < NS; ++n) {
-                    w[n] = __dadd_rd(tp.ix[n], PMVS_MAGIC_FLOOR);
-                    r[n] = __dadd_rd(tp.fy[n], PMVS_MAGIC_FLOOR);
-                }
-                const uint32_t *ad[NS];
-#pragma unroll
-                for (int n = 0; n < NS; ++n) {
-                    tp.px[n] = __double2loint(w[n]);
-                    ad[n] = quad[n / (GL * RB)] + (__double2loint(r[n]) * cols[n / (GL * RB)] + tp.px[n]);
-                }
-                ldg_group<NS>(ad, tp.q);
-#pragma unroll
-                for (int n = 0; n < NS; ++n) tp.fy[n] = tp.fy[n] - (r[n] - PMVS_MAGIC_FLOOR);
-            }
-            /* the pixel phase's own loads: reference colour and row weight of row GL*b + s */
-            double cref[RB], gy[RB];
-#pragma unroll
-            for (int b = 0; b < RB; ++b) {
-                cref[b] = lds_f64(rcol + 8u * GL * b);
-                gy[b] = lds_f64(ya[0] + (unsigned)jo + 16u * GL * b + 8u);
-            }
-            rcol += 8u * GL * RB;
-            /* ---- blend (column_blend) ---- */
-            double col[NS];
-#pragma unroll
-            for (int n = 0; n < NS; ++n) {
-                const int g00 = (int)__byte_perm(tp.q[n], 0, 0x4440), g01 = (int)__byte_perm(tp.q[n], 0, 0x4441);
-                const int g10 = (int)__byte_perm(tp.q[n], 0, 0x4442), g11 = (int)__byte_perm(tp.q[n], 0, 0x4443);
-                const int ndx = g00 - g01, idy = g10 - g00, ndxy = g10 - g11 - ndx;
-                const int k0 = tp.px[n] * ndx + g00, k1 = tp.px[n] * ndxy + idy;
-                col[n] = fma(tp.fy[n], fma(-tp.ix[n], cvt_a(ndxy), cvt_b(k1)), fma(-tp.ix[n], cvt_a(ndx), cvt_b(k0)));
-            }
-            /* ---- transpose: afterwards col[(c, b, t)] = view c*GL + (s ^ t) at row GL*b + s of the trip ---- */
-#pragma unroll
-            for (int n = 0; n < NS; ++n)
-                if (n % GL) col[n] = shfl_xor_f64(col[n], n % GL);
-            /* ---- pixel phase ---- */
-#pragma unroll
-            for (int b = 0; b < RB; ++b) {
-                double cv[NCH][GL];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                    for (int t = 0; t < GL; ++t) cv[c][t] = (FULL || real[c][t]) ? col[(c * RB + b) * GL + t] : 0.0;
-                double sum = tree_sum<GL>(cv[0]);
-#pragma unroll
-                for (int c = 1; c < NCH; ++c) sum += tree_sum<GL>(cv[c]);
-                sum += cref[b];
-                const double mean = sum * invV;
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                    for (int t = 0; t < GL; ++t) cv[c][t] = (FULL || real[c][t]) ? fabs(cv[c][t] - mean) : 0.0;
-                double dev = tree_sum<GL>(cv[0]);
-#pragma unroll
-                for (int c = 1; c < NCH; ++c) dev += tree_sum<GL>(cv[c]);
-                dev += fabs(cref[b] - mean);
-                const double wgt = gy[b] * exp_table_c(dev * dev * negK, tabA);                  /* patch.cpp:1030-1035 */
-                if (mlo & (1u << b)) {                                                         /* patch.cpp:986 */
-                    csw += wgt;
-                    cfit = fma(wgt, dev, cfit);
-                }
-            }
-            if (GL == 1) mlo = __funnelshift_r(mlo, mhi, RB), mhi >>= RB;
-            else mlo >>= RB;
+        for (int n = 0; n < NS; ++n) {
+            tp.ix[n] = fma(h1[n / (GL * RB)], y[n % (GL * RB)], A[n / (GL * RB)]) * r[n];
+            tp.fy[n] = fma(h4[n / (GL * RB)], y[n % (GL * RB)], B[n / (GL * RB)]) * r[n];       /* iy */
         }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            w[n] = __dadd_rd(tp.ix[n], PMVS_MAGIC_FLOOR);
+            r[n] = __dadd_rd(tp.fy[n], PMVS_MAGIC_FLOOR);
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            tp.px[n] = __double2loint(w[n]);
+            tp.q[n] = __ldg(quad[n / (GL * RB)] + (__double2loint(r[n]) * cols[n / (GL * RB)] + tp.px[n]));
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) tp.fy[n] = tp.fy[n] - (r[n] - PMVS_MAGIC_FLOOR);
+    };
+    /* blend (column_blend) + transpose: afterwards col[(c, b, t)] = view c*GL + (s ^ t) at row GL*b + s of the trip */
+    auto blend = [&](const VlTaps<NS> &tp, double *col) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            const int g00 = (int)__byte_perm(tp.q[n], 0, 0x4440), g01 = (int)__byte_perm(tp.q[n], 0, 0x4441);
+            const int g10 = (int)__byte_perm(tp.q[n], 0, 0x4442), g11 = (int)__byte_perm(tp.q[n], 0, 0x4443);
+            const int ndx = g00 - g01, idy = g10 - g00, ndxy = g10 - g11 - ndx;
+            const int k0 = tp.px[n] * ndx + g00, k1 = tp.px[n] * ndxy + idy;
+            col[n] = fma(tp.fy[n], fma(-tp.ix[n], cvt_a(ndxy), cvt_b(k1)), fma(-tp.ix[n], cvt_a(ndx), cvt_b(k0)));
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n)
+            if (n % GL) col[n] = shfl_xor_f64(col[n], n % GL);
+    };
+    /* pixel side: column constants, accumulators */
+    double fit = 0, sw = 0, cfit = 0, csw = 0, gxv = 0;
+    unsigned mlo = 0, mhi = 0, rcol = 0;
+    auto pixel_column = [&](int i0) {
+        const int i = i0 + ci;
+        const bool colOk = i < nx;
+        const int ic = colOk ? i : nx - 1;
+        gxv = colOk ? lds_f64(gxA + 8u * ic) : 0.0;
+        const unsigned long long mk = lds_u64(mkA + 8u * ic) >> (FW * s);     /* bit b = row GL * b + s of this column */
+        mlo = (unsigned)mk;
+        mhi = (unsigned)(mk >> 32);
+        rcol = rcA + 8u * (unsigned)(ic * nyp + s);
+    };
+    /* pixel phase of the trip at byte offset jo: mean / deviations / weights / accumulation for row GL*b + s */
+    auto pixel = [&](const double *col, unsigned jo) {
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            const double cref = lds_f64(rcol + 8u * GL * b);
+            /* row factor of the distance weight, zero where the reference pixel is background (patch.cpp:986) */
+            double gy = 0.0;
+            if (mlo & (1u << b)) gy = lds_f64(ya[0] + jo + 16u * GL * b + 8u);
+            double cv[NCH][GL];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int t = 0; t < GL; ++t) cv[c][t] = (FULL || real[c][t]) ? col[(c * RB + b) * GL + t] : 0.0;
+            double sum = tree_sum<GL>(cv[0]);
+#pragma unroll
+            for (int c = 1; c < NCH; ++c) sum += tree_sum<GL>(cv[c]);
+            sum += cref;
+            const double mean = sum * invV;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int t = 0; t < GL; ++t) cv[c][t] = (FULL || real[c][t]) ? fabs(cv[c][t] - mean) : 0.0;
+            double dev = tree_sum<GL>(cv[0]);
+#pragma unroll
+            for (int c = 1; c < NCH; ++c) dev += tree_sum<GL>(cv[c]);
+            dev += fabs(cref - mean);
+            const double wgt = gy * exp_table_c(dev * dev * negK, tabA);                  /* patch.cpp:1030-1035 */
+            csw += wgt;
+            cfit = fma(wgt, dev, cfit);
+        }
+        rcol += 8u * GL * RB;
+        if (GL == 1) mlo = __funnelshift_r(mlo, mhi, RB), mhi >>= RB;
+        else mlo >>= RB;
+    };
+    auto close_column = [&]() {
         sw = fma(gxv, csw, sw);
         fit = fma(gxv, cfit, fit);
+        cfit = csw = 0;
+    };
+
+#if PMVS_VL_PIPE
+    /* trips in (column pass, row trip) order; the sample phase runs one trip ahead of the pixel phase */
+    const int tripsPerPass = (int)(END / STEP), T = ((nx + CP - 1) / CP) * tripsPerPass;
+    VlTaps<NS> tp;
+    int cs = 0, cp = 0;
+    unsigned js = 0, jp = 0;
+    sample_column(0);
+    pixel_column(0);
+    sample(0u, tp);
+    for (int t = 0; t < T - 1; ++t) {
+        double col[NS];
+        blend(tp, col);
+        js += STEP;
+        if (js >= END) {
+            js = 0;
+            cs += CP;
+            sample_column(cs);
+        }
+        sample(js, tp);
+        pixel(col, jp);
+        jp += STEP;
+        if (jp >= END) {
+            close_column();
+            jp = 0;
+            cp += CP;
+            pixel_column(cp);
+        }
     }
+    {
+        double col[NS];
+        blend(tp, col);
+        pixel(col, jp);
+        close_column();
+    }
+#else
+    for (int i0 = 0; i0 < nx; i0 += CP) {
+        sample_column(i0);
+        pixel_column(i0);
+        for (unsigned jo = 0; jo < END; jo += STEP) {
+            VlTaps<NS> tp;
+            double col[NS];
+            sample(jo, tp);
+            blend(tp, col);
+            pixel(col, jo);
+        }
+        close_column();
+    }
+#endif
     fitOut = warp_sum(fit) * invV;
     swOut = warp_sum(sw);
 }

@@ -494,8 +494,8 @@ __device__ __noinline__ void cta_remove_invisible(const DevScene &S, CtaS &c, do
         if (__any_sync(PMVS_FULL, oob)) {
             if (lane == 0) atomicOr(&p.flag, 1);
         }
-        const double n = sqrt(warp_sum(sum));                                          /* :384 */
-        for (int s = lane; s < total; s += 32) dst[s] = dst[s] / n;
+        const double rn = 1.0 / sqrt(warp_sum(sum));                                   /* :384; Mat /= s multiplies by 1./s */
+        for (int s = lane; s < total; s += 32) dst[s] = dst[s] * rn;
     }
     __syncthreads();
     if (p.flag) {                                                                     /* :244-247 */

@@ -5,10 +5,12 @@ unmodified reference PSO, compiled by oracle/Makefile into oracle/_ref/):
 
 pso_kat.json      outputs of the UNMODIFIED reference solver (TMVS/pso/psosolver.cpp, particle.cpp) on analytic
                   functions under the interposed counter-based rand() (oracle/ref_pso_shim.cpp).
-fitness_kat.json  PAIS::getFitness values of the f64 restatement on the seeded synthetic scene, each cross-checked
-                  here against the independent NumPy implementation (tests/np_reference.py) before being written.
+fitness_kat.json  PAIS::getFitness values of the f64 restatement on the seeded synthetic scene, each required to be BIT-IDENTICAL
+                  to the unmodified reference's own getFitness (oracle/_ref/libtmvs_ref.so: TMVS/mvs/patch.cpp compiled in place
+                  against oracle/cvshim) and cross-checked against the independent NumPy implementation (tests/np_reference.py)
+                  before being written.
 refine_kat.json   Patch::refine()+removeInvisibleCamera() outputs of the restatement driven by the unmodified
-                  reference solver, same scene.
+                  reference solver, same scene; likewise required to equal the unmodified reference's refine() bit for bit.
 Floats are stored as C99 hex strings (exact)."""
 import ctypes as C
 import hashlib
@@ -24,6 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import orc  # noqa: E402
+import ref_tmvs  # noqa: E402
 import np_reference  # noqa: E402
 from pmvs_b200 import abi, scene  # noqa: E402
 
@@ -88,10 +91,12 @@ def main():
     fk = dict(scene_sha256=scene_digest(sc), configs={})
     for name, c in fitness_configs(cfg).items():
         o = orc.Oracle(c, sc.records, seed=42)
+        ref = ref_tmvs.RefScene(c, sc.records, seed=42)
         entries = []
         for lod in (0, 1, 2):
             hy = scene.hypotheses_from_patches(sc, patches, c, lod=lod, seed=5 + lod, per_patch=3, spread=1.0 + lod)
             f = o.fitness_batch(hy)
+            assert [hx(v) for v in f] == [hx(v) for v in ref.fitness_batch(hy)], (name, lod)
             for h, v in zip(hy, f):
                 v2 = np_reference.fitness(sc.cams, c, h)
                 if v == abi.DBL_MAX or v2 == abi.DBL_MAX or v != v:
@@ -103,10 +108,16 @@ def main():
     json.dump(fk, open(os.path.join(HERE, "fitness_kat.json"), "w"), indent=1)
 
     o = orc.Oracle(cfg, sc.records, seed=42, use_ref_pso=True)
+    ref = ref_tmvs.RefScene(cfg, sc.records, seed=42)
     rk = dict(scene_sha256=scene_digest(sc), sets=[])
     for ptype, n, seed in ((abi.TYPE_EXPAND, 12, 31), (abi.TYPE_SEED, 4, 32)):
         ps = sc.patches(n, seed=seed, ptype=ptype, first_id=100 * ptype)
         out = o.refine_batch(ps, flags=abi.F_POST_REMOVE_INVISIBLE)
+        for q, w in zip(out, ref.refine_batch(ps, flags=abi.F_POST_REMOVE_INVISIBLE)):
+            assert ([hx(v) for v in q.center], [hx(v) for v in q.normal], hx(q.fitness), hx(q.correlation), hx(q.priority), q.drop, q.nCam,
+                    list(q.camIdx[:q.nCam]), q.LOD, q.refCamIdx, q.psoRuns) == \
+                   ([hx(v) for v in w.center], [hx(v) for v in w.normal], hx(w.fitness), hx(w.correlation), hx(w.priority), w.drop, w.nCam,
+                    list(w.camIdx[:w.nCam]), w.LOD, w.refCamIdx, w.psoRuns)
         recs = []
         for q in out:
             recs.append(dict(center=[hx(v) for v in q.center], normal=[hx(v) for v in q.normal], fitness=hx(q.fitness),
