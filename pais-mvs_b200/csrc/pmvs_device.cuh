@@ -975,7 +975,17 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned a) {
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
     return v;
 }
-__device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(PMVS_FULL, v, m); }
+/* butterfly shuffle of a double IN PLACE (both halves keep their registers: no pair-repacking moves around the SHFLs) */
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+    asm volatile("{ .reg .b32 lo, hi;\n\t"
+                 "mov.b64 {lo, hi}, %0;\n\t"
+                 "shfl.sync.bfly.b32 lo, lo, %1, 0x1f, 0xffffffff;\n\t"
+                 "shfl.sync.bfly.b32 hi, hi, %1, 0x1f, 0xffffffff;\n\t"
+                 "mov.b64 %0, {lo, hi}; }"
+                 : "+d"(v)
+                 : "r"(m));
+    return v;
+}
 
 /* exp(x) of the difference weight for -700 <= x <= 0 as exp_table, with its constants in the constant bank (operands
  * of the fma, no register or uniform-register traffic) */
@@ -1024,11 +1034,22 @@ struct VlTaps {
     int px[N];
 };
 
+#ifndef PMVS_VL_DP4A
+#define PMVS_VL_DP4A 1
+#endif
+#ifndef PMVS_VL_F2I
+#define PMVS_VL_F2I 1
+#endif
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {      /* sum of (unsigned byte of a) * (signed byte of b) + c */
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 #ifndef PMVS_VL_RB
 #define PMVS_VL_RB 2            /* row blocks (of GL rows) per trip of the view-lane loop */
 #endif
 #ifndef PMVS_VL_PIPE
-#define PMVS_VL_PIPE 1          /* 1: software-pipelined trips (tap loads of trip t+1 issued before the pixel phase of trip t) */
+#define PMVS_VL_PIPE 0          /* 1: software-pipelined trips (tap loads of trip t+1 issued before the pixel phase of trip t) */
 #endif
 
 template <int GL, int NCH, int RB, bool FULL>
@@ -1115,12 +1136,18 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
         }
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
+#if !PMVS_VL_F2I
             w[n] = __dadd_rd(tp.ix[n], PMVS_MAGIC_FLOOR);
+#endif
             r[n] = __dadd_rd(tp.fy[n], PMVS_MAGIC_FLOOR);
         }
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
+#if PMVS_VL_F2I
+            tp.px[n] = __double2int_rd(tp.ix[n]);          /* floor on the conversion unit (F2I.F64.FLOOR): the FP64 / integer dispatch is the loop's bound */
+#else
             tp.px[n] = __double2loint(w[n]);
+#endif
             tp.q[n] = __ldg(quad[n / (GL * RB)] + (__double2loint(r[n]) * cols[n / (GL * RB)] + tp.px[n]));
         }
 #pragma unroll
@@ -1130,9 +1157,17 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
     auto blend = [&](const VlTaps<NS> &tp, double *col) {
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
+#if PMVS_VL_DP4A
+            /* tap differences as byte dot products (IDP.4A.U8.S8): taps (g00, g01, g10, g11) . signed weights */
+            const int ndx = dp4a_us(tp.q[n], 0x0000ff01, 0);                   /* g00 - g01 */
+            const int ndxy = dp4a_us(tp.q[n], (int)0xff0101ffu, 0);            /* -g00 + g01 + g10 - g11 */
+            const int idy = dp4a_us(tp.q[n], 0x000100ff, 0);                   /* g10 - g00 */
+            const int g00 = (int)(tp.q[n] & 0xffu);
+#else
             const int g00 = (int)__byte_perm(tp.q[n], 0, 0x4440), g01 = (int)__byte_perm(tp.q[n], 0, 0x4441);
             const int g10 = (int)__byte_perm(tp.q[n], 0, 0x4442), g11 = (int)__byte_perm(tp.q[n], 0, 0x4443);
             const int ndx = g00 - g01, idy = g10 - g00, ndxy = g10 - g11 - ndx;
+#endif
             const int k0 = tp.px[n] * ndx + g00, k1 = tp.px[n] * ndxy + idy;
             col[n] = fma(tp.fy[n], fma(-tp.ix[n], cvt_a(ndxy), cvt_b(k1)), fma(-tp.ix[n], cvt_a(ndx), cvt_b(k0)));
         }
@@ -1193,6 +1228,14 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
         cfit = csw = 0;
     };
 
+    /* PMVS_VL_FENCE: a never-taken branch after the sample phase. ptxas schedules inside basic blocks: without the block
+     * boundary it sinks every tap load next to its first use (a rolling schedule, ~20 instructions between LDG and PRMT) and
+     * the warp stalls on each of them; with it, all tap loads of a trip are in flight before the first one is consumed */
+#ifndef PMVS_VL_FENCE
+#define PMVS_VL_FENCE 0
+#endif
+    const bool never = S.cfg.patchRadius < 0;
+#define PMVS_FENCE_BLOCK() do { if (PMVS_VL_FENCE && never) { fit = -fit; sw = -sw; } } while (0)
 #if PMVS_VL_PIPE
     /* trips in (column pass, row trip) order; the sample phase runs one trip ahead of the pixel phase */
     const int tripsPerPass = (int)(END / STEP), T = ((nx + CP - 1) / CP) * tripsPerPass;
@@ -1212,6 +1255,7 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
             sample_column(cs);
         }
         sample(js, tp);
+        PMVS_FENCE_BLOCK();
         pixel(col, jp);
         jp += STEP;
         if (jp >= END) {
@@ -1235,6 +1279,7 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
             VlTaps<NS> tp;
             double col[NS];
             sample(jo, tp);
+            PMVS_FENCE_BLOCK();
             blend(tp, col);
             pixel(col, jo);
         }
