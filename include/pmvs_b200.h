@@ -50,7 +50,10 @@ extern "C" {
 
 /* per-patch status bits (out.status); 0 = nothing unusual */
 #define PMVS_S_TOO_MANY_VIEWS      1u  /* expandVisibleCamera found > PMVS_MAX_VIEWS cameras: patch dropped */
-#define PMVS_S_TOO_MANY_PARTICLES  2u  /* TYPE_SEED with 2*particleNum > 64 (patch.cpp:192): patch dropped */
+#define PMVS_S_TOO_MANY_PARTICLES  2u  /* reserved (rounds before 2: TYPE_SEED with 2*particleNum > 64); seeds now run the
+                                          reference's 2*particleNum particles for every accepted particleNum (<= 64) */
+#define PMVS_S_BAD_CAMERA          4u  /* a camIdx entry is not a camera of the scene: patch dropped (device-resident
+                                          inputs only; pmvs_refine_batch rejects such host records with PMVS_E_ARG) */
 
 /*
  * Byte-for-byte the reference's MvsConfig (TMVS/mvs/mvs.h:19-72) as laid out by MSVC/gcc x64:

@@ -271,13 +271,23 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
         if (idx >= n) break;
         if (tid == 0) {
             patch_from_in(in[idx], c.p);
-            if (c.p.type == PMVS_TYPE_SEED && S.cfg.particleNum * 2 > PMVS_MAX_PARTICLES) {   /* patch.cpp:192 needs 2P particles */
-                c.p.status |= PMVS_S_TOO_MANY_PARTICLES;
+            /* records this launch cannot hold are dropped in-band with a status bit instead of being evaluated:
+             * more camera entries than the scene's view tables were carved for (duplicate indices in a caller's list),
+             * or an index that is not a camera of the scene (corrupt .mvs / raw C-ABI caller) */
+            if (in[idx].nCam > a.vcap || in[idx].nCam < 0) {
+                c.p.status |= PMVS_S_TOO_MANY_VIEWS;
                 c.p.drop = 1;
+                c.p.nCam = 0;
             }
+            for (int i = 0; i < c.p.nCam; ++i)
+                if ((int)c.p.camIdx[i] >= S.nCams) {
+                    c.p.status |= PMVS_S_BAD_CAMERA;
+                    c.p.drop = 1;
+                }
+            if (c.p.status & PMVS_S_BAD_CAMERA) c.p.nCam = 0;
         }
         __syncthreads();
-        if (!(c.p.status & PMVS_S_TOO_MANY_PARTICLES)) {
+        if (!c.p.drop) {
             if ((flags & PMVS_F_EXPAND_VISIBLE) && c.p.type == PMVS_TYPE_EXPAND) cta_expand_visible(S, c.p);
             cta_refine(S, c, sDistW, W, W0.H, W0.xs, W0.ys, corr, hp);
             __syncthreads();
@@ -319,9 +329,10 @@ struct TestEval {
         __syncwarp();
     }
 };
+#define PMVS_PSO_TEST_MAX 64          /* particle rows of the test ABI's `particles` output */
 struct PsoTestS {
     PsoS pso;
-    ParticleS part[PMVS_MAX_PARTICLES];
+    ParticleS part[PMVS_PSO_TEST_MAX];
     MoveS mv;
     double init[3];
 };
@@ -334,7 +345,7 @@ struct PsoTestProblem {
 struct PsoTestResult {
     double gbest[3], gbestFitness;
     int iterations, _pad;
-    double particles[PMVS_MAX_PARTICLES][8];
+    double particles[PMVS_PSO_TEST_MAX][8];
 };
 __global__ void __launch_bounds__(512) pso_test_kernel(int n, const PsoTestProblem *__restrict__ prob, PsoTestResult *__restrict__ res) {
     __shared__ PsoTestS s;
@@ -386,6 +397,7 @@ struct pmvs_ctx {
     size_t scratchStride = 0;
     int scratchCtas = 0;
     int *dCounter = nullptr;
+    cudaEvent_t lastLaunch = nullptr;    /* refine launches of one context share its work counters and scratch slabs: they are serialised */
     void *dIn = nullptr, *dOut = nullptr;
     size_t dInBytes = 0, dOutBytes = 0;
     int64_t launches = 0;
@@ -430,8 +442,8 @@ static std::vector<double> dist_weight(const PmvsConfig &cfg) {
 static int check_config(pmvs_ctx *ctx, const PmvsConfig &cfg) {
     if (cfg.patchRadius < 0 || cfg.patchRadius > PMVS_MAX_RADIUS)
         return fail(ctx, PMVS_E_UNSUPPORTED, "patchRadius must be in [0, " + std::to_string(PMVS_MAX_RADIUS) + "]");
-    if (cfg.particleNum < 1 || cfg.particleNum > PMVS_MAX_PARTICLES)
-        return fail(ctx, PMVS_E_UNSUPPORTED, "particleNum must be in [1, " + std::to_string(PMVS_MAX_PARTICLES) + "]");
+    if (cfg.particleNum < 1 || cfg.particleNum > PMVS_MAX_PARTICLE_NUM)
+        return fail(ctx, PMVS_E_UNSUPPORTED, "particleNum must be in [1, " + std::to_string(PMVS_MAX_PARTICLE_NUM) + "]");
     if (cfg.maxIteration < 0) return fail(ctx, PMVS_E_ARG, "maxIteration < 0");
     if (!(cfg.lodRatio > 0.0 && cfg.lodRatio <= 1.0)) return fail(ctx, PMVS_E_ARG, "lodRatio must be in (0,1]");
     return PMVS_OK;
@@ -500,6 +512,7 @@ void pmvs_destroy(pmvs_ctx *ctx) {
     if (ctx->dDistW) cudaFree(ctx->dDistW);
     if (ctx->dScratch) cudaFree(ctx->dScratch);
     if (ctx->dCounter) cudaFree(ctx->dCounter);
+    if (ctx->lastLaunch) cudaEventDestroy(ctx->lastLaunch);
     if (ctx->dIn) cudaFree(ctx->dIn);
     if (ctx->dOut) cudaFree(ctx->dOut);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -855,10 +868,14 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
     int nChunks = ctx->smCount < PMVS_MAX_CHUNKS ? ctx->smCount : PMVS_MAX_CHUNKS;
     if (n < 4 * grid) nChunks = 1;
     if (const char *envL = getenv("PMVS_LOCAL")) { if (atoi(envL) == 0) nChunks = 1; }      /* tuning / A-B */
+    /* a launch on another stream must not overlap the previous one of this context (shared counters / scratch) */
+    if (!ctx->lastLaunch) CK(cudaEventCreateWithFlags(&ctx->lastLaunch, cudaEventDisableTiming));
+    else CK(cudaStreamWaitEvent(st, ctx->lastLaunch, 0));
     CK(cudaMemsetAsync(ctx->dCounter, 0, sizeof(int) * PMVS_MAX_CHUNKS, st));
     fn<<<grid, NW * 32, pl.total, st>>>(ctx->scene, to_args(pl), n, d_in, d_out, flags, ctx->dCounter, nChunks);
     ctx->launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->lastLaunch, st));
     return PMVS_OK;
 }
 
@@ -874,10 +891,12 @@ int pmvs_refine_batch(pmvs_ctx *ctx, int n, const PmvsPatchIn *in, PmvsPatchOut 
     if (!ctx || ctx->device < 0) return PMVS_E_ARG;
     if (n < 0 || (n > 0 && (!in || !out))) return fail(ctx, PMVS_E_ARG, "bad arguments to pmvs_refine_batch");
     if (n == 0) return PMVS_OK;
-    if (ctx->cfg.particleNum * 2 > PMVS_MAX_PARTICLES)
-        for (int i = 0; i < n; ++i)
-            if (in[i].type == PMVS_TYPE_SEED)
-                return fail(ctx, PMVS_E_UNSUPPORTED, "seed patches need 2*particleNum <= " + std::to_string(PMVS_MAX_PARTICLES));
+    for (int i = 0; i < n; ++i) {       /* host buffers can be validated up front (the device-resident call flags such records in-band) */
+        if (in[i].nCam < 0 || in[i].nCam > PMVS_MAX_VIEWS) return fail(ctx, PMVS_E_ARG, "patch " + std::to_string(i) + ": nCam out of range");
+        for (int k = 0; k < in[i].nCam; ++k)
+            if ((int)in[i].camIdx[k] >= ctx->nCams)
+                return fail(ctx, PMVS_E_ARG, "patch " + std::to_string(i) + ": camera index " + std::to_string(in[i].camIdx[k]) + " is not a camera of this scene");
+    }
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_buffers(ctx, sizeof(PmvsPatchIn) * (size_t)n, sizeof(PmvsPatchOut) * (size_t)n);
     if (rc) return rc;
@@ -982,7 +1001,7 @@ int pmvs_pso_test(pmvs_ctx *ctx, int n, const double *L, const double *U, const 
     CK(cudaSetDevice(ctx->device));
     std::vector<PsoTestProblem> pr(n);
     for (int i = 0; i < n; ++i) {
-        if (P[i] < 1 || P[i] > PMVS_MAX_PARTICLES) return fail(ctx, PMVS_E_UNSUPPORTED, "P out of range");
+        if (P[i] < 1 || P[i] > PMVS_PSO_TEST_MAX) return fail(ctx, PMVS_E_UNSUPPORTED, "P out of range");
         for (int d = 0; d < 3; ++d) {
             pr[i].L[d] = L[3 * i + d];
             pr[i].U[d] = U[3 * i + d];
@@ -1015,7 +1034,7 @@ int pmvs_pso_test(pmvs_ctx *ctx, int n, const double *L, const double *U, const 
         for (int d = 0; d < 3; ++d) gbest[3 * i + d] = hr[i].gbest[d];
         gbestFitness[i] = hr[i].gbestFitness;
         iterations[i] = hr[i].iterations;
-        if (particles) memcpy(particles + (size_t)i * PMVS_MAX_PARTICLES * 8, hr[i].particles, sizeof(hr[i].particles));
+        if (particles) memcpy(particles + (size_t)i * PMVS_PSO_TEST_MAX * 8, hr[i].particles, sizeof(hr[i].particles));
     }
     return PMVS_OK;
 }

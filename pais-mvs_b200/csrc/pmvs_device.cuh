@@ -24,7 +24,8 @@
 #include "../../include/pmvs_b200.h"
 #include "pmvs_rng.h"
 
-#define PMVS_MAX_PARTICLES 64
+#define PMVS_MAX_PARTICLES 128        /* swarm size: seeds run 2 * particleNum particles (patch.cpp:192) */
+#define PMVS_MAX_PARTICLE_NUM 64     /* MvsConfig.particleNum accepted by pmvs_create */
 #define PMVS_MAX_RADIUS 31
 #define PMVS_MAX_PS (2 * PMVS_MAX_RADIUS + 1)
 #define PMVS_FULL 0xffffffffu

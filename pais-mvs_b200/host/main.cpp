@@ -111,6 +111,7 @@ int main(int argc, char **argv) {
         return 2;
     }
     if (!outDir.empty() && outDir[outDir.size() - 1] != '/') outDir += "/";
+
     if (!imageDir.empty() && imageDir[imageDir.size() - 1] != '/') imageDir += "/";
 
     MvsConfig config;
@@ -123,6 +124,7 @@ int main(int argc, char **argv) {
     mvs.rngSeed = seed;
     mvs.autosaveSeconds = autosave;
     mvs.verbose = verbose;
+    mvs.outDir = outDir;
     mvs.mergeSlots = mergeSlots;
     mvs.imageDir = imageDir;
 

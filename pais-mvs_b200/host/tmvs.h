@@ -90,6 +90,8 @@ public:
     uint64_t rngSeed = 42;
     double autosaveSeconds = 5.0;      /* minimum spacing of auto_save.mvs checkpoints */
     bool verbose = false;
+    bool warnedViews = false;            /* one warning when a seed lists more than PMVS_MAX_VIEWS cameras */
+    std::string outDir;                  /* prefix of the files the driver writes on its own (auto_save.mvs) */
     std::string imageDir;              /* prefix for camera image files */
     long refinedCount = 0;             /* patches sent through refine() */
     double gpuSeconds = 0;             /* inside pmvs_refine_batch calls */

@@ -586,6 +586,10 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
         r.type = p.type;
         r.id = p.id;
         const std::vector<int> &cams = parentCams ? (*parentCams)[i] : p.camIdx;
+        if (cams.size() > PMVS_MAX_VIEWS && !warnedViews) {
+            warnedViews = true;
+            fprintf(stderr, "tmvs: patch %d lists %zu cameras; only the first %d are used (PMVS_MAX_VIEWS)\n", p.id, cams.size(), PMVS_MAX_VIEWS);
+        }
         r.nCam = (int)std::min<size_t>(cams.size(), PMVS_MAX_VIEWS);
         for (int k = 0; k < r.nCam; ++k) r.camIdx[k] = (uint16_t)cams[k];
     }
@@ -852,7 +856,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             Clock::time_point ts0 = Clock::now();
             lastSave = ts0;
             saveTime = patches.size() / 500;
-            writeMVS("auto_save.mvs");
+            writeMVS((outDir + "auto_save.mvs").c_str());
             tSave += std::chrono::duration<double>(Clock::now() - ts0).count();
         }
     }
@@ -1130,6 +1134,7 @@ bool MVS::loadNVM(const char *fileName, bool nvm2) {   /* fileloader.cpp:251-325
                     int idx, feat;
                     double x, y;
                     if (!(ps >> idx >> feat >> x >> y) || idx < 0 || idx >= (int)cameras.size()) { err = "NVM: bad measurement"; return false; }
+                    if (std::find(p.camIdx.begin(), p.camIdx.end(), idx) != p.camIdx.end()) continue;   /* one measurement per camera: a view enters the cost once */
                     p.camIdx.push_back(idx);
                     p.imgPoint.push_back(x + cameras[idx].cols / 2);
                     p.imgPoint.push_back(y + cameras[idx].rows / 2);
@@ -1200,6 +1205,7 @@ bool MVS::loadMVS(const char *fileName) {   /* fileloader.cpp:403-472 */
                 for (int k = 0; k < camNum; ++k) {
                     int idx = 0;
                     file.read((char *)&idx, sizeof(int));
+                    if (!file || idx < 0 || idx >= (int)cameras.size()) { err = "MVS: patch record names a camera the file does not hold"; return false; }
                     p.camIdx.push_back(idx);
                 }
                 file.read((char *)&p.fitness, sizeof(double));

@@ -9,6 +9,8 @@ TYPE_SEED, TYPE_EXPAND = 0, 1
 F_POST_REMOVE_INVISIBLE = 1
 F_EXPAND_VISIBLE = 2
 S_TOO_MANY_VIEWS = 1
+S_BAD_CAMERA = 4
+E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
 
 DBL_MAX = 1.7976931348623157e308
 

@@ -18,6 +18,7 @@ import os
 import numpy as np
 import pytest
 
+import named_configs
 import orc
 import refine_cases
 from pmvs_b200 import abi, scene
@@ -253,6 +254,81 @@ def test_refine_vs_oracle(case):
     print("%s: %d patches, %d kept, %d with views removed, worst relative deviation %.3g" % (case, n, kept, removed, worst))
     if case in ("wide_arc", "occluded"):
         assert removed > 0 or kept < n
+
+
+@pytest.mark.parametrize("k,scale", [(1, 1.0), (2, 1.0), (3, 1.0), (4, 0.5), (5, 0.25)])
+def test_named_config_vs_oracle(k, scale):
+    """BASELINE.json configs[0..4]: 64 patches each through Patch::refine() + removeInvisibleCamera() with expandVisibleCamera,
+    CUDA path vs oracle — visibility lists, LOD, reference camera, swarm iteration and evaluation counts identical, geometry
+    within 1e-4 (north_star). configs[0..2] at their named image sizes; configs[3] / [4] at the named view count, radius,
+    weights and swarm on half / quarter size images (host synthesis of 64 x 4000x3000 takes minutes)."""
+    c, cfg, sc = named_configs.build(k, scale)
+    n = c["check"]
+    patches = sc.patches(n, seed=5678)
+    flags = abi.F_POST_REMOVE_INVISIBLE | abi.F_EXPAND_VISIBLE
+    o = orc.Oracle(cfg, sc.records, seed=42, use_ref_pso=orc.ref_lib() is not None)
+    want = o.refine_batch(patches, flags=flags, patch_threads=os.cpu_count() or 1)
+    with PatchRefiner(cfg, sc.records, seed=42) as pr:
+        got = pr.refine(patches, flags=flags)
+    worst = compare_refine(got, want)
+    kept = sum(1 for q in want if not q.drop)
+    views = sum(q.nCam for q in want if not q.drop) / max(kept, 1)
+    print("%s (x%.2f): %d patches, %d kept, %.1f views kept on average, worst relative deviation %.3g" % (c["name"], scale, n, kept, views, worst))
+    assert kept >= n // 2
+
+
+def test_seed_swarm_larger_than_64_particles():
+    """patch.cpp:192: seeds run 2 * particleNum particles for 2 * maxIteration — also when that exceeds 64 (particleNum = 40)."""
+    cfg = abi.readme_config()
+    cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD = 7, 15, 7 / 3.0, 2
+    cfg.particleNum, cfg.maxIteration = 40, 12
+    sc = scene.SynthScene(cfg, nviews=5, width=400, height=300, seed=21, with_edge=True, tex_size=1024)
+    patches = sc.patches(6, seed=5, ptype=abi.TYPE_SEED)
+    o = orc.Oracle(cfg, sc.records, seed=42, use_ref_pso=orc.ref_lib() is not None)
+    want = o.refine_batch(patches, flags=abi.F_POST_REMOVE_INVISIBLE, patch_threads=6)
+    with PatchRefiner(cfg, sc.records, seed=42) as pr:
+        got = pr.refine(patches, flags=abi.F_POST_REMOVE_INVISIBLE)
+    compare_refine(got, want, max_late_flips=2)
+    assert all(q.status == 0 for q in got) and any(q.evaluations >= 80 * 2 for q in got)
+
+
+def test_capacity_limits_are_reported_not_overrun(small_scene):
+    """PMVS_MAX_RADIUS / particleNum limits fail pmvs_create with PMVS_E_UNSUPPORTED; a record with more camera entries than
+    the scene has cameras, or with an index that is not a camera, never reaches the kernels' view tables."""
+    from pmvs_b200 import lib as pmvs_lib
+    cfg, sc = small_scene
+    for field, value in (("patchRadius", 32), ("particleNum", 65), ("particleNum", 0)):
+        bad = abi.PmvsConfig.from_buffer_copy(cfg)
+        setattr(bad, field, value)
+        bad.patchSize = 2 * bad.patchRadius + 1
+        with pytest.raises(pmvs_lib.PmvsError) as e:
+            PatchRefiner(bad, sc.records, seed=42)
+        assert e.value.code == abi.E_UNSUPPORTED
+    patches = sc.patches(4, seed=3)
+    with PatchRefiner(cfg, sc.records, seed=42) as pr:
+        good = pr.refine(patches)
+        dup = sc.patches(4, seed=3)
+        dup[1].nCam = 7                                   # 5-camera scene: duplicate entries
+        for kk in range(7):
+            dup[1].camIdx[kk] = kk % 5
+        out = pr.refine(dup)
+        assert out[1].drop == 1 and out[1].status & abi.S_TOO_MANY_VIEWS and out[1].fitness == abi.DBL_MAX
+        for i in (0, 2, 3):
+            assert bytes(out[i]) == bytes(good[i])
+        bad = sc.patches(4, seed=3)
+        bad[2].camIdx[1] = 9                              # not a camera of the scene
+        with pytest.raises(pmvs_lib.PmvsError) as e:
+            pr.refine(bad)
+        assert e.value.code == abi.E_ARG
+        # the device-resident call cannot look at the records first: the kernel flags them in-band
+        import torch
+        d_in = torch.frombuffer(bytearray(bytes(bad)), dtype=torch.uint8).cuda()
+        d_out = torch.zeros(C.sizeof(abi.PmvsPatchOut) * 4, dtype=torch.uint8, device="cuda")
+        pr.refine_device(4, d_in.data_ptr(), d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        rec = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=scene.PATCH_OUT_DTYPE)
+        assert rec["drop"][2] == 1 and rec["status"][2] & abi.S_BAD_CAMERA
+        assert rec["drop"][0] == good[0].drop and rec["fitness"][0] == good[0].fitness
 
 
 def test_refine_properties_full_size():

@@ -16,18 +16,7 @@ from pmvs_b200 import abi, scene  # noqa: E402
 from pmvs_b200.api import PatchRefiner  # noqa: E402
 from test_gpu_parity import compare_refine  # noqa: E402
 
-CONFIGS = {
-    1: dict(name="configs[0]: 5 views 640x480, patchRadius=7, 1 pyramid level, adaptive weights off", views=5, w=640, h=480, r=7, levels=1,
-            weights=(0, 0, 0), P=15, I=30, n=8192, check=32),
-    2: dict(name="configs[1]: 5 views 1600x1200, patchRadius=15, 3 pyramid levels, adaptive distance+difference on", views=5, w=1600, h=1200,
-            r=15, levels=3, weights=(1, 1, 0), P=15, I=30, n=8192, check=32),
-    3: dict(name="configs[2]: 16 views 1600x1200, patchRadius=15, PSO 32 particles x 50 iters, visibleCorrelation=0.7", views=16, w=1600,
-            h=1200, r=15, levels=3, weights=(1, 1, 0), P=32, I=50, n=2048, check=16),
-    4: dict(name="configs[3]: 32 views 1920x1080, patchRadius=15, adaptiveGradient on", views=32, w=1920, h=1080, r=15, levels=3,
-            weights=(1, 1, 1), P=15, I=30, n=2048, check=16),
-    5: dict(name="configs[4]: 64 views 4000x3000, patchRadius=21, full adaptive weighting", views=64, w=4000, h=3000, r=21, levels=3,
-            weights=(1, 1, 1), P=15, I=30, n=1024, check=16),
-}
+from named_configs import CONFIGS  # noqa: E402
 
 
 def run(k):
