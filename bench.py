@@ -96,34 +96,108 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def traffic_per_launch(args, n):
-    """dram read+write bytes of one refine_kernel launch from the committed ncu capture (profiles/r1_traffic.json),
-    valid only for the launch size it was captured with; --traffic overrides."""
+def committed_profile():
+    """Counters of the committed ncu --set full capture of refine_kernel for the CURRENT build (profiles/r2_profile.json,
+    written by tools/ncu_profile_json.py): issue-slot, FP64-pipe and conversion-unit utilisation, dram bytes per launch."""
+    p = os.path.join(ROOT, "profiles", "r2_profile.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return {}
+
+
+def traffic_per_launch(args, n, prof):
+    """dram read+write bytes of one refine_kernel launch from the committed capture, valid only for the launch size it was
+    captured with; --traffic overrides."""
     if args.traffic is not None:
         return args.traffic
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(p):
-        t = json.load(open(p))
-        if t.get("patches") == n:
-            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    t = prof.get("traffic", {})
+    if t.get("patches") == n:
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
     return None
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, sc, n_patches, threads, seed=42, first_id=0, patch_seed=5678):
-    """The reference's CPU algorithm on host cores: f64 restatement of patch.cpp driven by the UNMODIFIED reference
-    solver when oracle/_ref is present (else the restated solver), patches spread over `threads` OpenMP threads."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import orc
-    use_ref = orc.ref_lib() is not None
-    o = orc.Oracle(cfg, sc.records, seed=seed, use_ref_pso=use_ref)
-    ps = sc.patches(n_patches, seed=patch_seed, first_id=first_id)
-    t0 = time.perf_counter()
-    out = o.refine_batch(ps, flags=abi.F_POST_REMOVE_INVISIBLE, patch_threads=threads)
-    dt = time.perf_counter() - t0
-    kept = sum(1 for q in out if not q.drop)
-    return dt, kept, ("unmodified reference PSO (oracle/_ref) + f64 restatement of patch.cpp" if use_ref else
-                      "f64 restatement (oracle/) of patch.cpp + psosolver.cpp")
+# The CPU arm. kind "reference": the UNMODIFIED reference (TMVS/mvs/patch.cpp + TMVS/pso/psosolver.cpp ... compiled in place
+# into oracle/_ref/libtmvs_ref.so against oracle/cvshim). kind "port": the f64 restatement (oracle/liborc.so) when that
+# library is absent. Two arrangements are timed:
+#   all cores        the reference's serial per-patch code in one worker PROCESS per host core (the reference keeps its
+#                    scene in a process-wide singleton), patches spread over the workers: the most the reference's code
+#                    can do with the box — this is the arm's `value`;
+#   own structure    the reference as it ships: patches serial, OpenMP over the particles of one swarm
+#                    (psosolver.cpp:113,122,222) with every host thread — reported beside it.
+_REF_SCENE = None
+
+
+def _ref_worker(job):
+    lo, hi, seed, first_id, total = job
+    ps = _REF_SCENE[1].patches(total, seed=seed, first_id=first_id)
+    sub = (abi.PmvsPatchIn * (hi - lo))(*[ps[i] for i in range(lo, hi)])
+    out = _REF_SCENE[0].refine_batch(sub, flags=abi.F_POST_REMOVE_INVISIBLE)
+    return sum(1 for q in out if not q.drop)
+
+
+class CpuArm:
+    def __init__(self, cfg, sc):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        import ref_tmvs
+        global _REF_SCENE
+        self.cores = os.cpu_count() or 1
+        self.cfg, self.sc = cfg, sc
+        self.pool = None
+        if ref_tmvs.lib() is not None:
+            self.kind = "reference"
+            self.how = "unmodified reference (TMVS/mvs/patch.cpp, TMVS/pso/psosolver.cpp ... compiled against oracle/cvshim: oracle/_ref/libtmvs_ref.so)"
+            self.ref = ref_tmvs.RefScene(cfg, sc.records, seed=42)
+            _REF_SCENE = (self.ref, sc)
+            import multiprocessing as mp
+            self.pool = mp.get_context("fork").Pool(self.cores)          # workers inherit the scene singleton
+        else:
+            self.kind = "port"
+            use_ref = orc.ref_lib() is not None
+            self.how = ("unmodified reference PSO (oracle/_ref/libpso_ref.so) + f64 restatement of patch.cpp (oracle/liborc.so)" if use_ref
+                        else "f64 restatement (oracle/liborc.so) of patch.cpp + psosolver.cpp")
+            self.orc = orc.Oracle(cfg, sc.records, seed=42, use_ref_pso=use_ref)
+
+    def all_cores(self, n, seed=5678, first_id=0):
+        """n candidate patches over every host core -> seconds, kept"""
+        t0 = time.perf_counter()
+        if self.pool is not None:
+            per = (n + self.cores - 1) // self.cores
+            jobs = [(lo, min(lo + per, n), seed, first_id, n) for lo in range(0, n, per)]
+            kept = sum(self.pool.map(_ref_worker, jobs))
+        else:
+            out = self.orc.refine_batch(self.sc.patches(n, seed=seed, first_id=first_id), flags=abi.F_POST_REMOVE_INVISIBLE, patch_threads=self.cores)
+            kept = sum(1 for q in out if not q.drop)
+        return time.perf_counter() - t0, kept
+
+    def own_structure(self, n, seed=5678):
+        """patches serial, OpenMP over particles with every host thread -> seconds"""
+        ps = self.sc.patches(n, seed=seed)
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self.ref.set_threads(self.cores)
+            self.ref.refine_batch(ps, flags=abi.F_POST_REMOVE_INVISIBLE)
+            self.ref.set_threads(1)
+        else:
+            self.orc.refine_batch(ps, flags=abi.F_POST_REMOVE_INVISIBLE, patch_threads=1, pso_threads=self.cores)
+        return time.perf_counter() - t0
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+    def baseline_record(self, value, n, seconds, own_n, own_seconds):
+        return {"value": value, "unit": UNIT, "cores": self.cores, "kind": self.kind,
+                "sample": "%d candidate patches of the same workload per step, one serial worker process per host core (%d), %.1f s; %s"
+                          % (n, self.cores, seconds, self.how),
+                "reference_structure": {"value": own_n / own_seconds, "unit": UNIT, "threads": self.cores,
+                                        "sample": "%d patches one after the other, OpenMP over the particles of each swarm "
+                                                  "(TMVS/pso/psosolver.cpp:113,122,222), %.1f s" % (own_n, own_seconds)}}
 
 
 def run_reference(args):
@@ -132,21 +206,24 @@ def run_reference(args):
         return 0
     cfg = bench_config()
     sc = make_scene(cfg, args.views, args.width, args.height)
-    cores = os.cpu_count() or 1
-    n = args.cpu_patches if args.cpu_patches > 0 else max(cores * 128, 64)
+    arm = CpuArm(cfg, sc)
+    cores = arm.cores
+    n = args.cpu_patches if args.cpu_patches > 0 else max(cores * 64, 64)          # ~4-6 s per step
     times = []
     for s in range(args.warmup + args.steps):
-        dt, kept, how = cpu_reference_run(cfg, sc, n, cores, patch_seed=5678 + s)
+        dt, kept = arm.all_cores(n, seed=5678 + s)
         if s >= args.warmup:
             times.append(dt)
+    own_n = max(cores * 2, 16)
+    own_dt = arm.own_structure(own_n)
+    arm.close()
     total = sum(times)
     value = n * len(times) / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "patches_per_step": n, "particles": cfg.particleNum, "iterations": cfg.maxIteration},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d candidate patches per step, OpenMP over patches on %d host threads; %s" % (n, cores, how)},
+            "cpu_baseline": arm.baseline_record(value, n, total / len(times), own_n, own_dt),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -185,36 +262,59 @@ def run_gpu(args):
     sc = make_scene(cfg, args.views, args.width, args.height)
     V = len(sc.cams)
     n = args.patches
+    cpu_rec = None
+    if world == 1 and not args.no_cpu_baseline:
+        # the CPU baseline runs first: its worker processes are forked before this process holds a CUDA context
+        arm = CpuArm(cfg, sc)
+        ncpu = args.cpu_patches if args.cpu_patches > 0 else max(arm.cores * 160, 256)     # ~10-20 s of CPU work
+        dt, ckept = arm.all_cores(ncpu)
+        own_n = max(arm.cores * 2, 16)
+        own_dt = arm.own_structure(own_n)
+        arm.close()
+        cpu_rec = arm.baseline_record(ncpu / dt, ncpu, dt, own_n, own_dt)
     pr = PatchRefiner(cfg, sc.records, device=local, seed=42)
 
-    in_bytes, out_bytes = C.sizeof(abi.PmvsPatchIn) * n, C.sizeof(abi.PmvsPatchOut) * n
+    REC = C.sizeof(abi.PmvsPatchOut)
+    in_bytes, out_bytes = C.sizeof(abi.PmvsPatchIn) * n, REC * n
     total_steps = args.warmup + args.steps
     # a different candidate set per step; resident in HBM before the timed region
     host_in = [sc.patches(n, seed=5678 + 1000 * rank + s, first_id=(rank * total_steps + s) * n) for s in range(total_steps)]
     d_in = [torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(dev) for h in host_in]
-    d_out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+    d_out = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]          # double-buffered: the exchange of step s
+    d_rec = [torch.empty((n, shard.RECORD_DOUBLES), dtype=torch.float64, device=dev) for _ in range(2)]   # overlaps the kernel of step s+1
+    d_all = [torch.empty((world * n, shard.RECORD_DOUBLES), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    d_cnt = torch.zeros(3, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: kernel, events and NCCL all on it
-    torch.cuda.set_stream(stream)
+    sK = torch.cuda.Stream(device=dev)              # refine kernel + events
+    sX = torch.cuda.Stream(device=dev)              # record pack + NCCL all-gather (the exchange between expansion rounds)
+    torch.cuda.set_stream(sK)
     flags = abi.F_POST_REMOVE_INVISIBLE
 
-    fit_off, drop_off = abi.PmvsPatchOut.fitness.offset, abi.PmvsPatchOut.drop.offset
-
-    def exchange():
-        """Exchange step between expansion rounds: every rank's converged records (centre, normal, fitness, drop)."""
-        rec = d_out.view(n, C.sizeof(abi.PmvsPatchOut))
-        geo = rec[:, :48].contiguous().view(torch.float64)
-        fit = rec[:, fit_off:fit_off + 8].contiguous().view(torch.float64)
-        drp = rec[:, drop_off:drop_off + 4].contiguous().view(torch.int32).double()
-        return shard.allgather_records(torch.cat([geo, fit, drp], dim=1), world * n, rank, world)
-
-    def one_pass(s):
-        pr.refine_device(n, d_in[s].data_ptr(), d_out.data_ptr(), flags, stream=stream.cuda_stream)
+    def one_pass(s, timed):
+        """refine step s on sK; pack its exchange records and (N > 1) all-gather them on sX, overlapping the next step's kernel"""
+        b = s & 1
+        if timed[b] is not None:
+            sK.wait_event(timed[b])                 # the exchange that last read d_out[b] is done
+        flush.zero_()                               # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(sK)
+        pr.refine_device(n, d_in[s].data_ptr(), d_out[b].data_ptr(), flags, stream=sK.cuda_stream)
+        e1.record(sK)
+        sX.wait_event(e1)
+        pr.pack_records_device(n, d_out[b].data_ptr(), d_rec[b].data_ptr(), d_cnt.data_ptr(), stream=sX.cuda_stream)
         if world > 1:
-            exchange()
+            with torch.cuda.stream(sX):
+                dist.all_gather_into_tensor(d_all[b], d_rec[b])
+        done = torch.cuda.Event()
+        done.record(sX)
+        timed[b] = done
+        return e0, e1
 
+    pending = [None, None]
     for s in range(args.warmup):
-        one_pass(s)
+        one_pass(s, pending)
+    torch.cuda.synchronize()
+    d_cnt.zero_()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
@@ -222,62 +322,72 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    step_ms, kernel_ms, evals, wevals, kept = [], [], 0, 0, 0
     launches0 = pr.launch_count()
+    spans = []
+    t_first = torch.cuda.Event(enable_timing=True)
+    t_last = torch.cuda.Event(enable_timing=True)
+    t_first.record(sK)
     for s in range(args.warmup, total_steps):
-        flush.zero_()                                                      # L2 flush between timed iterations
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(stream)
-        pr.refine_device(n, d_in[s].data_ptr(), d_out.data_ptr(), flags, stream=stream.cuda_stream)
-        e1.record(stream)
-        if world > 1:
-            exchange()
-        e2.record(stream)
-        e2.synchronize()
-        step_ms.append(e0.elapsed_time(e2))
-        kernel_ms.append(e0.elapsed_time(e1))
-        o = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=scene.PATCH_OUT_DTYPE)
-        evals += int(o["evaluations"].sum())
-        wevals += int(o["windowEvaluations"].sum())
-        kept += int((o["drop"] == 0).sum())
+        spans.append(one_pass(s, pending))
+    for ev in pending:
+        if ev is not None:
+            sK.wait_event(ev)                       # join: the last exchanges are inside the timed region
+    t_last.record(sK)
+    t_last.synchronize()
     torch.cuda.synchronize()
     launches = pr.launch_count() - launches0          # kernels of this library launched inside the timed region
     if world > 1:
         dist.barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    kernel_ms = [a.elapsed_time(b) for a, b in spans]
 
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    counts = torch.tensor([evals, wevals, kept], dtype=torch.float64, device=dev)
+    total_ms = torch.tensor([t_first.elapsed_time(t_last)], dtype=torch.float64, device=dev)
+    counts = d_cnt.to(torch.float64)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     total_s = float(total_ms.item()) / 1e3
     value = world * n * args.steps / total_s
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed call)
-    pin_in = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
-    pin_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
-    e2e_t = []
-    for s in range(0 if args.no_e2e else total_steps):
-        pin_in.numpy()[:] = np.frombuffer(bytes(host_in[s]), dtype=np.uint8)
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed call); at N > 1 the
+    # exchange is inside too: records packed on the host, copied up, all-gathered, copied back
+    e2e_value, e2e_bytes = None, (in_bytes, out_bytes)
+    if not args.no_e2e:
+        pin_in = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
+        pin_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+        pin_rec = torch.empty((n, shard.RECORD_DOUBLES), dtype=torch.float64).pin_memory()
+        pin_all = torch.empty((world * n, shard.RECORD_DOUBLES), dtype=torch.float64).pin_memory() if world > 1 else None
+        e2e_t = []
+        for s in range(total_steps):
+            pin_in.numpy()[:] = np.frombuffer(bytes(host_in[s]), dtype=np.uint8)
+            flush.zero_()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = pr.L.pmvs_refine_batch(pr.h, n, C.cast(pin_in.data_ptr(), C.POINTER(abi.PmvsPatchIn)),
+                                        C.cast(pin_out.data_ptr(), C.POINTER(abi.PmvsPatchOut)), flags)
+            pr._check(rc)
+            if world > 1:
+                pin_rec.numpy()[:] = shard.pack_records(np.frombuffer(pin_out.numpy(), dtype=scene.PATCH_OUT_DTYPE))
+                d_rec[0].copy_(pin_rec, non_blocking=True)
+                dist.all_gather_into_tensor(d_all[0], d_rec[0])
+                pin_all.copy_(d_all[0], non_blocking=True)
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                e2e_t.append(dt)
+        e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rc = pr.L.pmvs_refine_batch(pr.h, n, C.cast(pin_in.data_ptr(), C.POINTER(abi.PmvsPatchIn)),
-                                    C.cast(pin_out.data_ptr(), C.POINTER(abi.PmvsPatchOut)), flags)
-        dt = time.perf_counter() - t0
-        pr._check(rc)
-        if s >= args.warmup:
-            e2e_t.append(dt)
-    e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(e2e_total.item()) if e2e_t else None
+            dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+            e2e_bytes = (in_bytes + n * 64, out_bytes + world * n * 64)
+        e2e_value = world * n * args.steps / float(e2e_total.item())
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
+        prof = committed_profile()
         bpe = alg_bytes_per_eval(cfg, V)
         k_ms = sum(kernel_ms) / len(kernel_ms)
         wev_per_launch = counts[1].item() / (world * args.steps)
@@ -287,24 +397,26 @@ def run_gpu(args):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "patches_per_step_per_gpu": n, "views": V, "particles": cfg.particleNum,
                            "iterations": cfg.maxIteration, "l2": "flushed between timed steps (256 MiB memset)",
+                           "patches_counted": "every candidate refine() returned for, kept or dropped (SURVEY.md 8d); kept fraction beside it",
                            "converged_kept_fraction": counts[2].item() / (world * n * args.steps),
                            "evaluations_per_patch": counts[0].item() / (world * n * args.steps),
-                           "parallelism": "patches sharded by index over %d GPU(s); all-gather of converged records per pass" % world},
+                           "parallelism": "patches sharded by index over %d GPU(s); per pass the converged records {centre, normal, fitness, drop} "
+                                          "are packed by one kernel and all-gathered over NCCL on a second stream, overlapping the next pass's kernel" % world},
                 "clocks": sampler.summary(),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1]},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "refine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic_per_launch(args, n),
+                             "frac": achieved / peak, "traffic": traffic_per_launch(args, n, prof),
                              "peak_source": peak_src,
                              "alg_bytes_per_eval": bpe, "window_evals_per_launch": wev_per_launch, "kernel_ms": k_ms,
-                             "note": "algorithmic tap-bytes model of SURVEY.md 8(d); not HBM-bound: issue slots 49 %, FP64 pipe 32 %, DRAM 1 % of peak — see DESIGN.md section 2"}}
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            ncpu = args.cpu_patches if args.cpu_patches > 0 else max(cores * 512, 256)     # ~10-20 s of CPU work
-            dt, ckept, how = cpu_reference_run(cfg, sc, ncpu, cores)
-            line["cpu_baseline"] = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d candidate patches of the same workload, OpenMP over patches on %d host threads, %.1f s; %s"
-                                              % (ncpu, cores, dt, how)}
+                             "issue_frac": prof.get("issue_active_frac"), "fp64_frac": prof.get("fp64_pipe_frac"), "xu_frac": prof.get("xu_pipe_frac"),
+                             "mix_bound_frac": prof.get("mix_bound_frac"),
+                             "note": "algorithmic tap-bytes model of SURVEY.md 8(d); the path is not HBM-bound (DRAM ~1 % of peak): the binding units are "
+                                     "instruction issue with a large FP64 share and the conversion unit — issue_frac / fp64_frac / xu_frac are the "
+                                     "utilisations in the committed ncu capture of this build (profiles/r2_profile.json), mix_bound_frac the roofline "
+                                     "fraction a pure-ALU microbenchmark of the loop's instruction mix reaches at any occupancy (tools/ubench): DESIGN.md section 2"}}
+        if cpu_rec is not None:
+            line["cpu_baseline"] = cpu_rec
         print(json.dumps(line))
     pr.close()
     if world > 1:
@@ -318,13 +430,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--patches", type=int, default=16384, help="candidate patches per GPU per step")
+    ap.add_argument("--patches", type=int, default=65536, help="candidate patches per GPU per step (BASELINE.md section 4: 65 536)")
     ap.add_argument("--views", type=int, default=5)
     ap.add_argument("--particles", type=int, default=0, help="override particleNum (0 = README config, 15)")
     ap.add_argument("--iterations", type=int, default=0, help="override maxIteration (0 = README config, 30)")
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
-    ap.add_argument("--cpu-patches", type=int, default=0, help="CPU sample size (0 = 128 per host core)")
+    ap.add_argument("--cpu-patches", type=int, default=0, help="CPU sample size per step (0 = 64 per host core for --impl reference, 160 for cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the host-buffer end-to-end leg")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")

@@ -225,6 +225,14 @@ int pmvs_refine_batch(pmvs_ctx *ctx, int n, const PmvsPatchIn *in, PmvsPatchOut 
 int pmvs_refine_batch_device(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatchOut *d_out,
                              uint32_t flags, void *cudaStream);
 
+/* The exchange record of a multi-GPU driver (SURVEY.md 8b `pmvs_allgather_patches`, 8e): packs the n device-resident
+ * results into 8 doubles per patch {centre 3, normal 3, fitness, drop} — the payload ranks all-gather between expansion
+ * rounds (the collective itself is the host's: ncclAllGather / torch.distributed on d_records). d_counters: NULL or three
+ * uint64 {evaluations, windowEvaluations, kept patches} the kernel ADDS this batch's totals to. Enqueued on `cudaStream`
+ * (NULL = the context's stream), not synchronised. */
+int pmvs_pack_records_device(pmvs_ctx *ctx, int n, const PmvsPatchOut *d_out, double *d_records, uint64_t *d_counters,
+                             void *cudaStream);
+
 /* Number of kernel launches issued by this context so far (bench.py "gpu_launches"). */
 int64_t pmvs_launch_count(const pmvs_ctx *ctx);
 

@@ -303,6 +303,13 @@ int ref_scene_create(const PmvsConfig *cfg, int nCams, const PmvsCamera *cams, u
     return 0;
 }
 
+/* threads of the reference's own OpenMP loops (over particles: psosolver.cpp:113,122,222). More than one makes its rand()
+ * calls race, as in the reference: timing only. */
+int ref_set_threads(int n) {
+    omp_set_num_threads(n > 1 ? n : 1);
+    return 0;
+}
+
 int ref_set_neighbor_radius(double r) {
     MVS::getInstance().neighborRadius = r;
     return 0;

@@ -50,6 +50,10 @@ class RefScene:
         self.ps = 2 * cfg.patchRadius + 1
         self.L.ref_scene_create(C.byref(cfg), self.n_cams, records, seed)
 
+    def set_threads(self, n):
+        """OpenMP threads of the reference's own loops (particles); > 1 is for timing only (racy rand(), as in the reference)."""
+        self.L.ref_set_threads(int(n))
+
     def set_neighbor_radius(self, r):
         self.L.ref_set_neighbor_radius(r)
 

@@ -306,6 +306,34 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
     }
 }
 
+/* ---- exchange record of the multi-GPU driver: {centre 3, normal 3, fitness, drop} as 8 doubles per patch ---------- */
+__global__ void pack_records_kernel(int n, const PmvsPatchOut *__restrict__ out, double *__restrict__ rec, unsigned long long *__restrict__ counters) {
+    unsigned long long ev = 0, wev = 0, kept = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const PmvsPatchOut &o = out[i];
+        double *r = rec + 8 * (size_t)i;
+        r[0] = o.center[0]; r[1] = o.center[1]; r[2] = o.center[2];
+        r[3] = o.normal[0]; r[4] = o.normal[1]; r[5] = o.normal[2];
+        r[6] = o.fitness;
+        r[7] = (double)o.drop;
+        ev += o.evaluations;
+        wev += o.windowEvaluations;
+        kept += o.drop ? 0 : 1;
+    }
+    if (counters) {
+        for (int off = 16; off > 0; off >>= 1) {
+            ev += __shfl_xor_sync(0xffffffffu, ev, off);
+            wev += __shfl_xor_sync(0xffffffffu, wev, off);
+            kept += __shfl_xor_sync(0xffffffffu, kept, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(counters, ev);
+            atomicAdd(counters + 1, wev);
+            atomicAdd(counters + 2, kept);
+        }
+    }
+}
+
 /* ---- swarm on analytic functions (test support) ------------------------------------------------------- */
 struct TestEval {
     int fn;
@@ -885,6 +913,20 @@ int pmvs_refine_batch_device(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, Pmvs
     if (n == 0) return PMVS_OK;
     CK(cudaSetDevice(ctx->device));
     return refine_launch(ctx, n, d_in, d_out, flags, cudaStream ? (cudaStream_t)cudaStream : ctx->stream);
+}
+
+int pmvs_pack_records_device(pmvs_ctx *ctx, int n, const PmvsPatchOut *d_out, double *d_records, uint64_t *d_counters, void *cudaStream) {
+    if (!ctx || ctx->device < 0) return PMVS_E_ARG;
+    if (n < 0 || (n > 0 && (!d_out || !d_records))) return fail(ctx, PMVS_E_ARG, "bad arguments to pmvs_pack_records_device");
+    if (n == 0) return PMVS_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : ctx->stream;
+    int grid = (n + 255) / 256;
+    if (grid > ctx->smCount * 8) grid = ctx->smCount * 8;
+    pack_records_kernel<<<grid, 256, 0, st>>>(n, d_out, d_records, (unsigned long long *)d_counters);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PMVS_OK;
 }
 
 int pmvs_refine_batch(pmvs_ctx *ctx, int n, const PmvsPatchIn *in, PmvsPatchOut *out, uint32_t flags) {

@@ -68,6 +68,11 @@ class PatchRefiner:
         self._check(self.L.pmvs_refine_batch_device(self.h, n, C.c_void_p(d_in), C.c_void_p(d_out), flags,
                                                     C.c_void_p(stream) if stream else None))
 
+    def pack_records_device(self, n, d_out, d_records, d_counters=None, stream=None):
+        """{centre, normal, fitness, drop} as 8 doubles per patch from device-resident results (the all-gather payload)."""
+        self._check(self.L.pmvs_pack_records_device(self.h, n, C.c_void_p(d_out), C.c_void_p(d_records),
+                                                    C.c_void_p(d_counters) if d_counters else None, C.c_void_p(stream) if stream else None))
+
     def launch_count(self):
         return int(self.L.pmvs_launch_count(self.h))
 

@@ -13,7 +13,7 @@ CSRC = os.path.join(PKG_ROOT, "csrc")
 
 # every symbol include/pmvs_b200.h declares
 SYMBOLS = ["pmvs_create", "pmvs_set_neighbor_radius", "pmvs_set_config", "pmvs_fitness_batch", "pmvs_refine_batch",
-           "pmvs_refine_batch_device", "pmvs_launch_count", "pmvs_pso_test", "pmvs_destroy", "pmvs_last_error",
+           "pmvs_refine_batch_device", "pmvs_pack_records_device", "pmvs_launch_count", "pmvs_pso_test", "pmvs_destroy", "pmvs_last_error",
            "pmvs_version", "pmvs_pyramid_levels", "pmvs_build_pyramid", "pmvs_neighbor_counts"]
 
 _LIB = None
@@ -54,6 +54,8 @@ def load():
     L.pmvs_refine_batch.argtypes = [vp, C.c_int, C.POINTER(abi.PmvsPatchIn), C.POINTER(abi.PmvsPatchOut), C.c_uint32]
     L.pmvs_refine_batch_device.restype = C.c_int
     L.pmvs_refine_batch_device.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, vp]
+    L.pmvs_pack_records_device.restype = C.c_int
+    L.pmvs_pack_records_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.pmvs_launch_count.restype = C.c_int64
     L.pmvs_launch_count.argtypes = [vp]
     L.pmvs_pso_test.restype = C.c_int
