@@ -196,9 +196,15 @@ namespace {
 uint64_t gSeed = 0;
 int gPatchId = 0, gRun = 0;
 uint64_t gKey = 0, gCtr = 0;
+bool gExpansion = false;          /* inside MVS::expansionPatches(): the patch under refinement is the one constructed last */
 }
+namespace PAIS { struct IdPeek { static int last() { return AbstractPatch::globalId - 1; } }; }
 extern "C" int rand(void) { return (int)pmvs_rand31(gKey, gCtr++); }
 extern "C" void srand(unsigned int) {          /* PsoSolver::setRandomSeed (psosolver.cpp:60-64): a new solver starts */
+    if (gExpansion) {                          /* expandCell (mvs.cpp:566-577): Patch expPatch(center, parent) took id = globalId++ */
+        const int id = PAIS::IdPeek::last();
+        if (id != gPatchId) { gPatchId = id; gRun = 0; }
+    }
     gKey = pmvs_stream_key(gSeed, gPatchId, gRun++);
     gCtr = 0;
 }
@@ -428,6 +434,64 @@ int ref_refine_batch(int n, const PmvsPatchIn *in, PmvsPatchOut *out, uint32_t f
         }
     }
     return 0;
+}
+
+
+/* ---- the caller side, unmodified: MVS::expansionPatches (mvs.cpp:233-275) with everything under it — expandNeighborCell,
+ * expandCell, getExpansionPatchCenter, skipNeighborCell, runtimeFiltering, insertPatch, deletePatch, the queue pops, cell
+ * maps, setNeighborRadius — after the seed loop of MVS::refineSeedPatches (:196-231), which is replayed here line by line
+ * only because the RNG stream has to be keyed by the seed's id (the reference seeds by wall clock). */
+int ref_run_reconstruction(int nSeeds, const PmvsPatchIn *seeds) {
+    Quiet q;
+    MVS &mvs = MVS::getInstance();
+    mvs.patches.clear();
+    mvs.deletedPatches.clear();
+    mvs.cellMaps.clear();
+    mvs.queue.clear();
+    for (int i = 0; i < nSeeds; ++i) {
+        const PmvsPatchIn &a = seeds[i];
+        mvs.patches.insert(std::pair<int, Patch>(a.id, make_patch(a.center, a.normal, a.normalS, a.nCam, a.camIdx, Patch::TYPE_SEED, a.id)));
+    }
+    AbstractPatch::globalId = nSeeds;                       /* seeds took ids 0..nSeeds-1 (abstractpatch.cpp:7-18) */
+    mvs.setNeighborRadius();                                /* refineSeedPatches, mvs.cpp:202 */
+    gExpansion = false;
+    for (std::map<int, Patch>::iterator it = mvs.patches.begin(); it != mvs.patches.end();) {
+        Patch &pth = it->second;
+        if (pth.getCameraNumber() < mvs.minCamNum) { it = mvs.deletePatch(pth); continue; }
+        gPatchId = pth.getId();
+        gRun = 0;
+        pth.refine();
+        pth.removeInvisibleCamera();
+        if (!mvs.runtimeFiltering(pth)) { it = mvs.deletePatch(pth); continue; }
+        ++it;
+    }
+    mvs.setNeighborRadius();
+    gExpansion = true;
+    gPatchId = -1;
+    mvs.expansionPatches();
+    gExpansion = false;
+    return (int)mvs.patches.size();
+}
+double ref_neighbor_radius(void) { return MVS::getInstance().neighborRadius; }
+/* patch k in id order: id, geometry, scores, cameras, image points; returns 0 past the end */
+int ref_get_patch(int k, int *id, double *center, double *normal, double *scores /*fitness, priority, correlation*/, int *nCam, int *camIdx,
+                  double *imgPoints, int *expanded) {
+    const MVS &mvs = MVS::getInstance();
+    if (k < 0 || k >= (int)mvs.patches.size()) return 0;
+    std::map<int, Patch>::const_iterator it = mvs.patches.begin();
+    std::advance(it, k);
+    const Patch &p = it->second;
+    *id = p.getId();
+    for (int d = 0; d < 3; ++d) { center[d] = p.getCenter()[d]; normal[d] = p.getNormal()[d]; }
+    scores[0] = p.getFitness();
+    scores[1] = p.getPriority();
+    scores[2] = p.getCorrelation();
+    *nCam = p.getCameraNumber();
+    for (int i = 0; i < *nCam && i < PMVS_MAX_VIEWS; ++i) camIdx[i] = p.getCameraIndices()[i];
+    const int np = (int)p.getImagePoints().size();
+    for (int i = 0; i < np && i < PMVS_MAX_VIEWS; ++i) { imgPoints[2 * i] = p.getImagePoints()[i][0]; imgPoints[2 * i + 1] = p.getImagePoints()[i][1]; }
+    *expanded = p.isExpanded() ? 1 : 0;
+    return 1 + np;
 }
 
 }   // extern "C"

@@ -37,6 +37,10 @@ def lib():
         L.ref_region_ratio.restype = C.c_double
         L.ref_region_ratio.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_refine_batch.argtypes = [C.c_int, C.POINTER(abi.PmvsPatchIn), C.POINTER(abi.PmvsPatchOut), C.c_uint32]
+        L.ref_run_reconstruction.argtypes = [C.c_int, C.POINTER(abi.PmvsPatchIn)]
+        L.ref_neighbor_radius.restype = C.c_double
+        L.ref_get_patch.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         _LIB = L
     return _LIB
 
@@ -96,3 +100,21 @@ class RefScene:
         out = (abi.PmvsPatchOut * n)()
         self.L.ref_refine_batch(n, patches, out, flags)
         return out
+
+    def run_reconstruction(self, seeds):
+        """The reference's own seed loop + MVS::expansionPatches() (mvs.cpp:196-275, unmodified) from these seed records
+        (ids 0..n-1). Returns the final patch container in id order: dicts of exact values."""
+        n = self.L.ref_run_reconstruction(len(seeds), seeds)
+        out = []
+        for k in range(n):
+            pid, nc, ex = C.c_int(), C.c_int(), C.c_int()
+            c, nr, sc = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_double * 3)()
+            ci, ip = (C.c_int * abi.MAX_VIEWS)(), (C.c_double * (2 * abi.MAX_VIEWS))()
+            r = self.L.ref_get_patch(k, C.byref(pid), c, nr, sc, C.byref(nc), ci, ip, C.byref(ex))
+            assert r > 0
+            out.append(dict(id=pid.value, center=list(c), normal=list(nr), fitness=sc[0], priority=sc[1], correlation=sc[2],
+                            cam_idx=list(ci[:nc.value]), img_point=[(ip[2 * i], ip[2 * i + 1]) for i in range(r - 1)], expanded=bool(ex.value)))
+        return out
+
+    def neighbor_radius(self):
+        return self.L.ref_neighbor_radius()
