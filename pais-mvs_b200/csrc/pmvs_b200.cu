@@ -9,6 +9,7 @@
  *                         reference solver)
  * There is no CPU fallback: every compute entry point needs an sm_100 device.
  */
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -569,6 +570,18 @@ static cudaError_t upload_u8(const uint8_t *host, int64_t hpitch, int cols, int 
 static cudaError_t resize_level(const DevU8 &src, double f, int dcols, int drows, DevU8 &dst, cudaStream_t st, int64_t *launches) {
     AreaTab tx, ty;
     const double scale = 1.0 / f;
+    const int iscale = cv_round(scale);
+    if (std::fabs(scale - iscale) < DBL_EPSILON) {            /* is_area_fast (OpenCV resize.cpp) */
+        cudaError_t e = cudaMallocPitch(&dst.p, &dst.pitch, (size_t)dcols, (size_t)drows);
+        if (e != cudaSuccess) return e;
+        dst.cols = dcols;
+        dst.rows = drows;
+        dim3 block(32, 8), grid((dcols + 31) / 32, (drows + 7) / 8);
+        resize_area_fast_kernel<<<grid, block, 0, st>>>(src.p, src.pitch, src.cols, src.rows, dst.p, dst.pitch, dcols, drows, iscale);
+        ++*launches;
+        e = cudaGetLastError();
+        return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+    }
     build_area_tab(src.cols, dcols, scale, tx);
     build_area_tab(src.rows, drows, scale, ty);
     cudaError_t e = cudaMallocPitch(&dst.p, &dst.pitch, (size_t)dcols, (size_t)drows);
@@ -608,7 +621,11 @@ static cudaError_t edge_level(const DevU8 &g, double *edge, unsigned long long *
     cudaError_t e = cudaMemcpyAsync(dMinMax, init, sizeof(init), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     dim3 grid((g.cols + 255) / 256, g.rows < 1024 ? g.rows : 1024);
-    edge_minmax_kernel<<<grid, 256, 0, st>>>(g.p, g.pitch, g.cols, g.rows, dMinMax);
+    {   /* the reduction pass: a few CTAs per SM striding the image, so the same-address atomics stay in the hundreds */
+        int gx = (g.cols + 255) / 256, gy = 1184 / gx;
+        gy = gy < 1 ? 1 : (gy > g.rows ? g.rows : gy);
+        edge_minmax_kernel<<<dim3(gx, gy), 256, 0, st>>>(g.p, g.pitch, g.cols, g.rows, dMinMax);
+    }
     edge_normalise_kernel<<<grid, 256, 0, st>>>(g.p, g.pitch, g.cols, g.rows, dMinMax, edge);
     *launches += 2;
     e = cudaGetLastError();

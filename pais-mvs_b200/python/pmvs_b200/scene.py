@@ -64,67 +64,20 @@ def camera_max_lod(cols, rows, cfg):
 # ---------------------------------------------------------------------------------------------------------
 # pyramids (camera.cpp:63-92)
 # ---------------------------------------------------------------------------------------------------------
-def _area_tab(ssize, dsize, scale):
-    """OpenCV's INTER_AREA table for one axis and a non-integer scale (imgproc computeResizeAreaTab): per destination
-    index the first source index, the tap count and the float32 weights."""
-    max_taps = int(math.ceil(scale)) + 2
-    start = np.zeros(dsize, dtype=np.int64)
-    count = np.zeros(dsize, dtype=np.int64)
-    W = np.zeros((dsize, max_taps), dtype=np.float32)
-    for dx in range(dsize):
-        fsx1 = dx * scale
-        fsx2 = fsx1 + scale
-        cell = min(scale, ssize - fsx1)
-        sx1 = int(math.ceil(fsx1))
-        sx2 = int(math.floor(fsx2))
-        sx2 = min(sx2, ssize - 1)
-        sx1 = min(sx1, sx2)
-        n, first = 0, sx1
-        if sx1 - fsx1 > 1e-3:
-            first = sx1 - 1
-            W[dx, n] = (sx1 - fsx1) / cell
-            n += 1
-        for sx in range(sx1, sx2):
-            W[dx, n] = 1.0 / cell
-            n += 1
-        if fsx2 - sx2 > 1e-3:
-            W[dx, n] = min(min(fsx2 - sx2, 1.0), cell) / cell
-            n += 1
-        start[dx], count[dx] = first, n
-    return start, count, W
-
-
 def resize_area(img, f):
-    """cv::resize(img, Size(), f, f, INTER_AREA) for u8 single-channel, f < 1 (camera.cpp:85): float32 weighted
-    horizontal sums per source row, then float32 weighted vertical sums, each accumulated in source order (the order
-    csrc/pmvs_pyramid.cuh and host/tmvs_lib.cpp use, so all three agree bit for bit), round half to even, saturate."""
-    rows, cols = img.shape
-    dcols, drows = int(np.rint(cols * f)), int(np.rint(rows * f))
-    scale = 1.0 / f
-    xs, xn, Wx = _area_tab(cols, dcols, scale)
-    ys, yn, Wy = _area_tab(rows, drows, scale)
-    src = img.astype(np.float32)
-    tmp = np.zeros((rows, dcols), dtype=np.float32)
-    for k in range(Wx.shape[1]):
-        m = k < xn
-        if not m.any():
-            break
-        tmp[:, m] = tmp[:, m] + Wx[m, k][None, :] * src[:, xs[m] + k]
-    out = np.zeros((drows, dcols), dtype=np.float32)
-    for k in range(Wy.shape[1]):
-        m = k < yn
-        if not m.any():
-            break
-        out[m, :] = out[m, :] + Wy[m, k][:, None] * tmp[ys[m] + k, :]
-    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+    """cv::resize(img, Size(), f, f, INTER_AREA) (camera.cpp:85) — by OpenCV itself: the synthetic scenes are built with the
+    library the reference uses (cv2 here is 4.x; its INTER_AREA code path is the 2.4 one). The restatement the device
+    kernels are checked against lives with the test infrastructure (oracle/orc_pyramid.py)."""
+    import cv2
+    return cv2.resize(np.ascontiguousarray(img), None, fx=f, fy=f, interpolation=cv2.INTER_AREA)
 
 
 def edge_image(grey):
-    """Sobel(ksize=1) gradient magnitude, min-max normalised (camera.cpp:71-78, 87-91). ksize=1 is the
-    [-1,0,1] central difference; the border is BORDER_REFLECT_101."""
-    g = np.pad(grey.astype(np.float64), 1, mode="reflect")
-    gx = g[1:-1, 2:] - g[1:-1, :-2]
-    gy = g[2:, 1:-1] - g[:-2, 1:-1]
+    """Sobel(ksize=1) gradient magnitude, min-max normalised (camera.cpp:71-78, 87-91), by OpenCV."""
+    import cv2
+    g = np.ascontiguousarray(grey)
+    gx = cv2.Sobel(g, cv2.CV_64F, 1, 0, ksize=1)
+    gy = cv2.Sobel(g, cv2.CV_64F, 0, 1, ksize=1)
     e = np.sqrt(gx * gx + gy * gy)
     mn, mx = e.min(), e.max()
     return np.ascontiguousarray((e - mn) / (mx - mn))

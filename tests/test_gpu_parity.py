@@ -395,21 +395,26 @@ def test_refine_independent_of_launch_configuration(small_scene):
 
 
 def test_pyramid_build_on_device():
-    """camera.cpp:63-92 on the GPU: bit-exact against the NumPy restatement (grey levels and f64 edge levels), odd
-    sizes included; and a context created from level 0 only evaluates exactly like one given every level."""
+    """camera.cpp:63-92 on the GPU: grey levels BIT-IDENTICAL to OpenCV's cv::resize(INTER_AREA) (cv2) and to the NumPy
+    restatement (oracle/orc_pyramid.py), f64 edge levels identical to cv::Sobel's; fractional scales (lodRatio 0.8, 0.7) and
+    the integer-scale path (lodRatio 0.5: 2x2 and 4x4 blocks), odd sizes included; and a context created from level 0 only
+    evaluates exactly like one given every level."""
+    import cv2
+    import orc_pyramid
     from pmvs_b200 import api
     from scipy.ndimage import gaussian_filter
     rng = np.random.RandomState(11)
     for (h, w) in ((389, 613), (480, 640)):
         img = np.clip(gaussian_filter(rng.rand(h, w), 1.5) * 900 - 320, 0, 255).astype(np.uint8)
-        cfg = abi.readme_config()
-        cfg.maxLOD = 6
-        want = scene.build_pyramid(img, cfg, True)
-        got = api.build_pyramid(img, cfg.lodRatio, cfg.maxLOD, with_edge=True)
-        assert len(got) == len(want) == 7
-        for l, ((g, e), (wg, we)) in enumerate(zip(got, want)):
-            assert g.shape == wg.shape and np.array_equal(g, wg), l
-            assert np.array_equal(e, we), l
+        for ratio, levels in ((0.8, 7), (0.7, 5), (0.5, 4)):
+            want = orc_pyramid.build_pyramid(img, ratio, levels - 1, True)
+            got = api.build_pyramid(img, ratio, levels - 1, with_edge=True)
+            assert len(got) == len(want) == levels
+            for l, ((g, e), (wg, we)) in enumerate(zip(got, want)):
+                assert g.shape == wg.shape and np.array_equal(g, wg), (ratio, l)
+                assert np.array_equal(e, we), (ratio, l)
+                if l > 0:
+                    assert np.array_equal(g, cv2.resize(img, None, fx=ratio ** l, fy=ratio ** l, interpolation=cv2.INTER_AREA)), (ratio, l)
     cfg = abi.readme_config()
     cfg.patchRadius, cfg.patchSize, cfg.distWeighting, cfg.maxLOD, cfg.adaptiveGradientEnable = 7, 15, 7 / 3.0, 2, 1
     sc = scene.SynthScene(cfg, nviews=5, width=400, height=300, seed=3, with_edge=True, tex_size=1024)

@@ -196,23 +196,23 @@ def test_dist_weight_table(small_scene):
 
 
 def test_pyramid_restatement_against_cv2():
-    """INTER_AREA resize and the Sobel(ksize=1) edge image (camera.cpp:71-92) against OpenCV 4.13 where available
-    (same algorithm family as the reference's 2.4.2; +-1 grey level for float rounding)."""
+    """The NumPy restatement of the Camera ctor's pyramid (oracle/orc_pyramid.py: INTER_AREA resize, fractional and integer
+    scales, and the Sobel(ksize=1) edge image, camera.cpp:71-92) is BIT-IDENTICAL to OpenCV's own cv::resize / cv::Sobel."""
     cv2 = pytest.importorskip("cv2")
+    import orc_pyramid
     rng = np.random.RandomState(5)
     from scipy.ndimage import gaussian_filter
-    img = np.clip(gaussian_filter(rng.rand(389, 613), 1.5) * 900 - 320, 0, 255).astype(np.uint8)
-    for l in (1, 2, 5):
-        f = 0.8 ** l
-        mine = scene.resize_area(img, f)
-        ref = cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_AREA)
-        assert mine.shape == ref.shape
-        assert np.abs(mine.astype(int) - ref.astype(int)).max() <= 1 and (mine != ref).mean() < 0.01
-    e = scene.edge_image(img)
-    gx = cv2.Sobel(img, cv2.CV_64F, 1, 0, ksize=1)
-    gy = cv2.Sobel(img, cv2.CV_64F, 0, 1, ksize=1)
-    m = np.sqrt(gx * gx + gy * gy)
-    assert np.array_equal(e, (m - m.min()) / (m.max() - m.min()))
+    for (h, w) in ((389, 613), (240, 320), (121, 203)):
+        img = np.clip(gaussian_filter(rng.rand(h, w), 1.5) * 900 - 320, 0, 255).astype(np.uint8)
+        for f in (0.8, 0.8 ** 2, 0.8 ** 5, 0.7, 0.5, 0.25, 1 / 3.0):
+            mine = orc_pyramid.resize_area(img, f)
+            ref = cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_AREA)
+            assert mine.shape == ref.shape and np.array_equal(mine, ref), (h, w, f)
+        e = orc_pyramid.edge_image(img)
+        gx = cv2.Sobel(img, cv2.CV_64F, 1, 0, ksize=1)
+        gy = cv2.Sobel(img, cv2.CV_64F, 0, 1, ksize=1)
+        m = np.sqrt(gx * gx + gy * gy)
+        assert np.array_equal(e, (m - m.min()) / (m.max() - m.min()))
 
 
 def test_homographies_are_the_plane_induced_maps(small_scene):
