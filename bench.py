@@ -27,14 +27,19 @@ sys.path.insert(0, os.path.join(ROOT, "pais-mvs_b200", "python"))
 
 import numpy as np  # noqa: E402
 
-from pmvs_b200 import abi, scene, shard  # noqa: E402
+from pmvs_b200 import abi, named_configs, scene, shard  # noqa: E402
 
 METRIC = "converged patches/sec (r=15, 5 views 1600x1200)"
 UNIT = "patches/s"
 WORKLOAD = "configs[1]: 5 views 1600x1200, patchRadius=15, 3 pyramid levels, adaptive distance+difference on"
 
 
+ARGS = None
+
+
 def bench_config():
+    if ARGS is not None and ARGS.config != 2:      # another of BASELINE.json's configs (the bench line stays configs[1])
+        return named_configs.config_of(ARGS.config)
     cfg = abi.readme_config()        # README.md:110-207 sample config.txt over TMVS.cpp:26-52 defaults
     cfg.patchRadius = 15
     cfg.patchSize = 31
@@ -45,7 +50,16 @@ def bench_config():
 
 
 def make_scene(cfg, views=5, width=1600, height=1200):
+    if ARGS is not None and ARGS.config != 2:
+        return named_configs.build(ARGS.config, ARGS.scale)[2]
     return scene.SynthScene(cfg, nviews=views, width=width, height=height, seed=1234)
+
+
+def workload_name():
+    if ARGS is not None and ARGS.config != 2:
+        c = named_configs.CONFIGS[ARGS.config]
+        return c["name"] + (" (images at %.2f x the named size: the work of one evaluation does not depend on it)" % ARGS.scale if ARGS.scale != 1.0 else "")
+    return WORKLOAD
 
 
 def alg_bytes_per_eval(cfg, V):
@@ -222,7 +236,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "patches_per_step": n, "particles": cfg.particleNum, "iterations": cfg.maxIteration},
+            "config": {"workload": workload_name(), "patches_per_step": n, "particles": cfg.particleNum, "iterations": cfg.maxIteration},
             "cpu_baseline": arm.baseline_record(value, n, total / len(times), own_n, own_dt),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -288,7 +302,7 @@ def run_gpu(args):
     sK = torch.cuda.Stream(device=dev)              # refine kernel + events
     sX = torch.cuda.Stream(device=dev)              # record pack + NCCL all-gather (the exchange between expansion rounds)
     torch.cuda.set_stream(sK)
-    flags = abi.F_POST_REMOVE_INVISIBLE
+    flags = abi.F_POST_REMOVE_INVISIBLE | (abi.F_EXPAND_VISIBLE if args.config != 2 else 0)
 
     def one_pass(s, timed):
         """refine step s on sK; pack its exchange records and (N > 1) all-gather them on sX, overlapping the next step's kernel"""
@@ -395,7 +409,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "patches_per_step_per_gpu": n, "views": V, "particles": cfg.particleNum,
+                "config": {"workload": workload_name(), "patches_per_step_per_gpu": n, "views": V, "particles": cfg.particleNum,
                            "iterations": cfg.maxIteration, "l2": "flushed between timed steps (256 MiB memset)",
                            "patches_counted": "every candidate refine() returned for, kept or dropped (SURVEY.md 8d); kept fraction beside it",
                            "converged_kept_fraction": counts[2].item() / (world * n * args.steps),
@@ -440,7 +454,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the host-buffer end-to-end leg")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configs[K-1]; 2 = the metric's configuration (default). Others are extra evidence, not the bench line")
+    ap.add_argument("--scale", type=float, default=1.0, help="with --config: image size relative to the named one")
     args = ap.parse_args()
+    global ARGS
+    ARGS = args
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: fewer than 3 warm-up steps", file=sys.stderr)
     return run_reference(args) if args.impl == "reference" else run_gpu(args)

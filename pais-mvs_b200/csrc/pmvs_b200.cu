@@ -45,17 +45,20 @@ __global__ void pack_quad_kernel(const uint8_t *__restrict__ grey, size_t pitch,
 /* carve the dynamic shared memory of one CTA */
 struct SmemPlan {
     size_t ctaOff, viewOff, distOff, warpOff, corrOff, refWinOff, total;
-    size_t perWarp;      /* doubles per warp: H + xs + ys + column constants */
-    int vcap, ps, nWarps, slotViews, nRefWin;
+    size_t perWarp;      /* doubles per warp: H + xs + ys + column constants + colour stash */
+    int vcap, ps, nWarps, slotViews, nRefWin, useVL, grad, stash;
 };
 /* nRefWin: reference windows (RefWin tables) the CTA holds — one per CTA (refine), one per warp (fitness), 0 = none */
-static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t headBytes, bool useVL, int nRefWin) {
+static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t headBytes, bool useVL, int nRefWin, bool grad) {
     SmemPlan pl;
     pl.vcap = vcap;
     pl.ps = ps;
     pl.nWarps = nWarps;
+    pl.useVL = useVL ? 1 : 0;
+    pl.grad = grad ? 1 : 0;
     pl.slotViews = PMVS_SLOT_VIEWS_OF(vcap, useVL);
     pl.nRefWin = nRefWin;
+    pl.stash = nRefWin ? PMVS_STASH_DOUBLES(vcap, useVL, grad) : 0;
     size_t off = 0;
     pl.ctaOff = off;
     off += (headBytes + 15) & ~(size_t)15;
@@ -65,19 +68,20 @@ static SmemPlan plan_smem(int vcap, int ps, int nWarps, bool withCorr, size_t he
     pl.distOff = off;
     off += sizeof(double) * ((size_t)PMVS_DIST_PAD(ps) + 64);     /* distance weights + exp table */
     pl.warpOff = off;
-    pl.perWarp = (((size_t)PMVS_HCAP(vcap) * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_HYP_DOUBLES + PMVS_COLV_DOUBLES_N(vcap, ps, pl.slotViews);
+    pl.perWarp = (((size_t)PMVS_HCAP(vcap) * 9 + 2 * (size_t)ps + 1) & ~(size_t)1) + PMVS_HYP_DOUBLES +
+                 PMVS_COLV_DOUBLES_N(vcap, ps, pl.slotViews, pl.useVL && nRefWin) + pl.stash;
     off += sizeof(double) * pl.perWarp * nWarps;
     pl.corrOff = off;
     if (withCorr && !PMVS_CORR_GLOBAL(vcap)) off += sizeof(double) * (size_t)vcap * vcap;
     off = (off + 15) & ~(size_t)15;
     pl.refWinOff = off;
-    off += sizeof(double) * PMVS_REFWIN_DOUBLES(ps) * (size_t)nRefWin;
+    off += sizeof(double) * PMVS_REFWIN_DOUBLES(ps, grad) * (size_t)nRefWin;
     pl.total = off;
     return pl;
 }
 struct SmemArgs {
     unsigned ctaOff, viewOff, distOff, warpOff, corrOff, perWarp, refWinOff;
-    int vcap, ps, slotViews, nRefWin;
+    int vcap, ps, slotViews, nRefWin, useVL, grad, stash;
 };
 static SmemArgs to_args(const SmemPlan &pl) {
     SmemArgs a;
@@ -92,22 +96,27 @@ static SmemArgs to_args(const SmemPlan &pl) {
     a.ps = pl.ps;
     a.slotViews = pl.slotViews;
     a.nRefWin = pl.nRefWin;
+    a.useVL = pl.useVL && pl.nRefWin;
+    a.grad = pl.grad;
+    a.stash = pl.stash;
     return a;
 }
+/* per-warp area: H | xs | ys | hyp | [slots | view table | rowf | rowi] (column-lane loop only) | colour stash */
 __device__ __forceinline__ WarpWork warp_work(unsigned char *smem, const SmemArgs &a, int warp) {
     double *base = (double *)(smem + a.warpOff) + (size_t)a.perWarp * warp;
     WarpWork W;
     W.H = base;
     W.xs = base + (size_t)PMVS_HCAP(a.vcap) * 9;
     W.ys = W.xs + a.ps;
-    W.colv = base + a.perWarp - PMVS_COLV_DOUBLES_N(a.vcap, a.ps, a.slotViews);
+    W.colv = base + a.perWarp - a.stash - PMVS_COLV_DOUBLES_N(a.vcap, a.ps, a.slotViews, a.useVL);
     W.hyp = W.colv - PMVS_HYP_DOUBLES;
     W.slotViews = a.slotViews;
     W._padw = 0;
-    W.gv = W.colv + PMVS_COLV_SLOTS_N(a.slotViews);
-    W.rowf = W.gv + PMVS_GV_DOUBLES_N(a.vcap, a.slotViews);
-    W.rowi = (int2 *)(W.rowf + PMVS_PS_PAD(a.ps));
+    W.gv = a.useVL ? nullptr : W.colv + PMVS_COLV_SLOTS_N(a.slotViews);
+    W.rowf = a.useVL ? nullptr : W.gv + PMVS_GV_DOUBLES_N(a.vcap, a.slotViews, a.useVL);
+    W.rowi = a.useVL ? nullptr : (int2 *)(W.rowf + PMVS_PS_PAD(a.ps));
     W.rw = nullptr;
+    W.stash = a.stash ? base + a.perWarp - a.stash : nullptr;
     return W;
 }
 
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(128) fitness_batch_kernel(const __grid_constan
     RefWin &R = ((FitWarpS *)(smem + a.ctaOff))[warp].rw;
     if (lane == 0) {
         E.view = (ViewS *)(smem + a.viewOff) + (size_t)warp * a.vcap;
-        if (a.nRefWin) carve_ref_win(R, (double *)(smem + a.refWinOff) + PMVS_REFWIN_DOUBLES(a.ps) * (size_t)warp, a.ps);
+        if (a.nRefWin) carve_ref_win(R, (double *)(smem + a.refWinOff) + PMVS_REFWIN_DOUBLES(a.ps, a.grad) * (size_t)warp, a.ps, a.grad != 0);
     }
     __syncthreads();
     WarpWork W = warp_work(smem, a, warp);
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(MAXT, MINB) refine_kernel(const __grid_constan
     WarpWork W = warp_work(smem, a, warp);
     const WarpWork W0 = warp_work(smem, a, 0);
     if (a.nRefWin) {
-        if (tid == 0) carve_ref_win(c.rw, (double *)(smem + a.refWinOff), a.ps);
+        if (tid == 0) carve_ref_win(c.rw, (double *)(smem + a.refWinOff), a.ps, a.grad != 0);
         W.rw = &c.rw;
     }
     int home = 0;
@@ -510,6 +519,7 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     {
         const char *envVL = getenv("PMVS_VL");          /* tuning / A-B: PMVS_VL=0 keeps the column-lane loop */
         s.useVL = (envVL && atoi(envVL) == 0) ? 0 : 1;
+        if (const char *envG = getenv("PMVS_ROWS_GLN")) s.useVL |= (atoi(envG) & 7) << 4;      /* tuning: lanes per pixel of fitness_vl_rows */
     }
     for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
     /* correlation scratch: one slab per resident CTA */
@@ -786,18 +796,24 @@ int pmvs_fitness_batch(pmvs_ctx *ctx, int n, const PmvsHypothesis *in, double *o
     int rc = ensure_buffers(ctx, sizeof(PmvsHypothesis) * (size_t)n, sizeof(double) * (size_t)n);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->dIn, in, sizeof(PmvsHypothesis) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    const int NW = 4;
-    const bool useVL = ctx->scene.useVL != 0;
-    SmemPlan pl = plan_smem(PMVS_MAX_VIEWS * NW, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW, false, 0);
-    /* the per-warp H area must hold PMVS_MAX_VIEWS homographies: plan with vcap = MAX_VIEWS for the warp area */
-    SmemPlan plw = plan_smem(PMVS_MAX_VIEWS, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW, false, 0);
-    pl.perWarp = plw.perWarp;
-    pl.slotViews = plw.slotViews;
-    pl.refWinOff = (pl.warpOff + sizeof(double) * pl.perWarp * NW + 15) & ~(size_t)15;
-    pl.nRefWin = useVL ? NW : 0;                                     /* one reference window per warp */
-    pl.total = pl.refWinOff + sizeof(double) * PMVS_REFWIN_DOUBLES(ctx->cfg.patchSize) * (size_t)pl.nRefWin;
+    const bool useVL = ctx->scene.useVL != 0, grad = ctx->cfg.adaptiveGradientEnable != 0;
+    /* per-warp contexts: NW EvalCtx + NW x MAX_VIEWS view records in the head / view areas, the per-warp area planned for
+     * MAX_VIEWS views, one reference window per warp */
+    int NW = 4;
+    SmemPlan pl;
+    for (;; NW >>= 1) {
+        pl = plan_smem(PMVS_MAX_VIEWS, ctx->cfg.patchSize, NW, false, sizeof(FitWarpS) * NW, useVL, useVL ? NW : 0, grad);
+        /* the view area must hold NW x MAX_VIEWS records: re-carve with the larger view table */
+        const size_t extraViews = sizeof(ViewS) * (size_t)PMVS_MAX_VIEWS * (NW - 1);
+        pl.distOff += extraViews;
+        pl.warpOff += extraViews;
+        pl.corrOff += extraViews;
+        pl.refWinOff += extraViews;
+        pl.total += extraViews;
+        if (pl.total <= 227 * 1024 || NW == 1) break;
+    }
+    if (pl.total > 227 * 1024) return fail(ctx, PMVS_E_UNSUPPORTED, "fitness kernel does not fit on an SM with this patch size");
     SmemArgs a = to_args(pl);
-    a.vcap = PMVS_MAX_VIEWS;
     CK(cudaFuncSetAttribute(fitness_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     int grid = (n + NW - 1) / NW;
     if (grid > ctx->smCount * 8) grid = ctx->smCount * 8;
@@ -823,7 +839,7 @@ static int refine_config(pmvs_ctx *ctx, int NW, RefineCfg &c) {
     c.NW = NW;
     const bool useVL = ctx->scene.useVL != 0;
     c.pl = plan_smem(ctx->vcap, ctx->cfg.patchSize, NW, true, ctaBytes + sizeof(ParticleS) * (size_t)nPart, useVL,
-                     (useVL && ctx->vcap >= 2 && ctx->vcap <= PMVS_VL_VIEWS) ? 1 : 0);
+                     (useVL && ctx->vcap >= 2) ? 1 : 0, ctx->cfg.adaptiveGradientEnable != 0);
     /* three register budgets of the same kernel: 96 registers (20 warps/SM, NW <= 5), 128 (16 warps/SM, NW <= 8,
      * or one 16-warp CTA). Measured (8192 patches, P = 15): 3 views 217k vs 199k patches/s and 5 views 142k vs 137k in
      * favour of 96 registers, 8 views 54.8k vs 57.3k in favour of 128 (the wider view loops spill), 12 views equal. */

@@ -45,11 +45,17 @@
 #define PMVS_COLV_VIEWS(vcap) ((vcap) > 16 ? 0 : ((vcap) < 2 ? 1 : ((vcap) - 1 > PMVS_SLOT_VIEWS ? PMVS_SLOT_VIEWS : (vcap) - 1)))
 #define PMVS_CORR_GLOBAL(vcap) ((vcap) > 16)   /* the V x V correlation table (+ V region ratios) in the CTA's global scratch */
 /* scenes the view-lane loop covers (<= 9 cameras) keep no slots either: only its rare fallbacks reach the old loop */
-#define PMVS_VL_VIEWS 9
-#define PMVS_SLOT_VIEWS_OF(vcap, useVL) (((useVL) && (vcap) <= PMVS_VL_VIEWS) ? 0 : PMVS_COLV_VIEWS(vcap))
+#define PMVS_VL_VIEWS 9                 /* views the register form of the view-lane loop covers (fitness_vl) */
+#define PMVS_SLOT_VIEWS_OF(vcap, useVL) ((useVL) ? 0 : PMVS_COLV_VIEWS(vcap))
+/* per-warp colour stash of the many-view / gradient form (fitness_vl_many): 4 doubles per lane and chunk of 4 views */
+#ifndef PMVS_VL_MANY_STASH
+#define PMVS_VL_MANY_STASH 0            /* 1: the stash form (fitness_vl_many); 0: the register form (fitness_vl_rows) — no stash */
+#endif
+#define PMVS_STASH_DOUBLES(vcap, useVL, grad) ((PMVS_VL_MANY_STASH && (useVL) && ((vcap) > PMVS_VL_VIEWS || (grad))) ? (((vcap) - 1 + 3) / 4) * 128 : 0)
 #define PMVS_COLV_SLOTS_N(slotViews) (3 * (slotViews) * 32)
-#define PMVS_GV_DOUBLES_N(vcap, slotViews) (((slotViews) > 0 && (vcap) - 1 <= (slotViews)) ? 6 * ((vcap) < 2 ? 1 : (vcap) - 1) : 12 * ((vcap) < 2 ? 1 : (vcap) - 1))
-#define PMVS_COLV_DOUBLES_N(vcap, ps, slotViews) (PMVS_COLV_SLOTS_N(slotViews) + PMVS_GV_DOUBLES_N(vcap, slotViews) + 2 * PMVS_PS_PAD(ps))
+/* useVL: no view table at all — the rare hypotheses the view-lane loop does not take go to the lane-strided loops */
+#define PMVS_GV_DOUBLES_N(vcap, slotViews, useVL) ((useVL) ? 0 : (((slotViews) > 0 && (vcap) - 1 <= (slotViews)) ? 6 * ((vcap) < 2 ? 1 : (vcap) - 1) : 12 * ((vcap) < 2 ? 1 : (vcap) - 1)))
+#define PMVS_COLV_DOUBLES_N(vcap, ps, slotViews, useVL) (PMVS_COLV_SLOTS_N(slotViews) + PMVS_GV_DOUBLES_N(vcap, slotViews, useVL) + ((useVL) ? 0 : 2 * PMVS_PS_PAD(ps)))
 #define PMVS_COLV_SLOTS(vcap) (3 * PMVS_COLV_VIEWS(vcap) * 32)
 /* compact table of the non-reference views. Slot mode (<= PMVS_SLOT_VIEWS of them): 6 doubles each — h1, h4, h7, quad
  * pointer, cols, spare; inline mode: 12 — h0..h8, quad pointer, cols, spare */
@@ -115,17 +121,20 @@ struct RefWin {
     double *gx;                  /* nx column factors of the distance weight */
     unsigned long long *mask;    /* nx: bit (64/gl) (j % gl) + j / gl = reference pixel of (column, row j) is not background */
     double *refc;                /* nx x nyp: the reference view's sample of every window position */
+    double *pw;                  /* gradient weighting on: nx x nyp per-pixel weights = distance weight x gradient weight
+                                    (patch.cpp:1030-1032, :1036-1038) x background mask; nullptr otherwise */
     int nx, ny, nyp, ok, gl, _pad;
 };
-/* doubles one RefWin's tables take for patch size ps: xs | gx | ysg | mask | refc */
-#define PMVS_REFWIN_DOUBLES(ps) (5 * (size_t)PMVS_PS_PAD8(ps) + (size_t)(ps) * PMVS_NYP(ps))
-__device__ __forceinline__ void carve_ref_win(RefWin &R, double *base, int ps) {
+/* doubles one RefWin's tables take for patch size ps: xs | gx | ysg | mask | refc | pw */
+#define PMVS_REFWIN_DOUBLES(ps, grad) (5 * (size_t)PMVS_PS_PAD8(ps) + (size_t)(ps) * PMVS_NYP(ps) * ((grad) ? 2 : 1))
+__device__ __forceinline__ void carve_ref_win(RefWin &R, double *base, int ps, bool grad) {
     const int pp = PMVS_PS_PAD8(ps);
     R.xs = base;
     R.gx = base + pp;
     R.ysg = (double2 *)(base + 2 * pp);
     R.mask = (unsigned long long *)(base + 4 * pp);
     R.refc = base + 5 * pp;
+    R.pw = grad ? R.refc + (size_t)ps * PMVS_NYP(ps) : nullptr;
     R.nyp = PMVS_NYP(ps);
     R.nx = R.ny = 0;
     R.ok = 0;
@@ -144,6 +153,7 @@ struct WarpWork {
     double *rowf;   /* PMVS_PS_PAD(ps): fractional part of each window row in the reference view */
     int2 *rowi;     /* PMVS_PS_PAD(ps): {floor(y) * refCols, 2 * (cvRound(y) - floor(y))} per window row */
     const RefWin *rw;   /* the patch's reference window (nullptr: none built) */
+    double *stash;      /* PMVS_STASH_DOUBLES: per-lane colours of the many-view loop (nullptr: none) */
 };
 
 __device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -1291,9 +1301,299 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
     swOut = warp_sum(sw);
 }
 
+/*
+ * The view-lane loop for any number of views (V = 2..64) and for gradient weighting: GL = 4 lanes per window column, four
+ * rows per trip, the non-reference views in chunks of four — lane s of a quad samples view 4c + s of chunk c (homography
+ * row read from shared memory per chunk and trip: 9 loads and 3 fma for four samples, where the column-lane loop paid them
+ * per sample), the quad transposes, and lane s then holds the four colours of chunk c at row s. They go into the
+ * cross-view sum and into the warp's colour stash (shared memory, 32 B per lane and chunk); once every chunk is in, the mean
+ * is known and a second walk over the STASH — not over the images — forms the absolute deviations (patch.cpp:1022-1027):
+ * one sampling pass instead of the two of fitness_columns_many. GRAD: the per-pixel weight table of the reference window
+ * (distance x gradient x mask) replaces the separable distance factors and the mask bits.
+ */
+__device__ __forceinline__ void sts_f64x2(unsigned a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory"); }
+__device__ __forceinline__ double2 lds_f64x2_v(unsigned a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+
+template <bool GRAD>
+__device__ __noinline__ void fitness_vl_many(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *__restrict__ Hw,
+                                             const double *__restrict__ sExpT, double *stash, double &fitOut, double &swOut) {
+    const int lane = threadIdx.x & 31, s = lane & 3, ci = lane >> 2;
+    const int V = E.V, NG = V - 1, NCH = (NG + 3) >> 2, refV = E.refView, nx = R.nx, nyp = R.nyp;
+    const int ny = (R.ny + 3) & ~3;
+    const unsigned END = 16u * (unsigned)ny;
+    const unsigned hA = smem_addr(Hw), xsA = smem_addr(R.xs), gxA = smem_addr(R.gx), ysgA = smem_addr(R.ysg), mkA = smem_addr(R.mask);
+    const unsigned rcA = smem_addr(R.refc), pwA = GRAD ? smem_addr(R.pw) : 0u, tabA = smem_addr(sExpT), viewA = smem_addr(E.view);
+    const unsigned stA = smem_addr(stash) + 16u * (unsigned)lane;        /* chunk c: pair 0 at stA + 1024 c, pair 1 at stA + 1024 c + 512 */
+    const double invV = 1.0 / (double)V;
+    const double negK = S.cfg.adaptiveDifferenceEnable ? -(invV * invV) / S.cfg.diffWeighting : 0.0;
+    unsigned ya[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) ya[t] = ysgA + 16u * (unsigned)(s ^ t);
+
+    double fit = 0, sw = 0;
+    for (int i0 = 0; i0 < nx; i0 += 8) {
+        const int i = i0 + ci;
+        const bool colOk = i < nx;
+        const int ic = colOk ? i : nx - 1;
+        const double x = lds_f64(xsA + 8u * ic);
+        const double gxv = colOk ? (GRAD ? 1.0 : lds_f64(gxA + 8u * ic)) : 0.0;
+        unsigned mlo = 0;
+        if (!GRAD) mlo = (unsigned)(lds_u64(mkA + 8u * ic) >> (16 * s));
+        unsigned pix = 8u * (unsigned)(ic * nyp + s);                      /* byte offset of (column, row s) in refc / pw */
+        double cfit = 0, csw = 0;
+        for (unsigned jo = 0; jo < END; jo += 64u) {
+            double y[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) y[t] = lds_f64(ya[t] + jo);
+            double sum = 0;
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                int k = 4 * c + s;
+                if (k >= NG) k = 0;                                         /* padding lane: samples view 0 again, discarded below */
+                const int v = k + (k >= refV ? 1 : 0);
+                const unsigned h = hA + 72u * (unsigned)v, va = viewA + (unsigned)(sizeof(ViewS) * v);
+                const double h1 = lds_f64(h + 8u), h4 = lds_f64(h + 32u), h7 = lds_f64(h + 56u);
+                const double A = fma(lds_f64(h), x, lds_f64(h + 16u)), B = fma(lds_f64(h + 24u), x, lds_f64(h + 40u)),
+                             Cc = fma(lds_f64(h + 48u), x, lds_f64(h + 64u));
+                const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(va + (unsigned)offsetof(ViewS, quad));
+                const int cols = lds_s32(va + (unsigned)offsetof(ViewS, cols));
+                double w[4], r[4], e[4], ix[4], fy[4];
+                int px[4];
+                uint32_t q[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) w[t] = fma(h7, y[t], Cc);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[t]) : "d"(w[t]));
+#pragma unroll
+                for (int t = 0; t < 4; ++t) e[t] = fma(-w[t], r[t], 1.0);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) e[t] = fma(e[t], e[t], e[t]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r[t] = fma(r[t], e[t], r[t]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    ix[t] = fma(h1, y[t], A) * r[t];
+                    fy[t] = fma(h4, y[t], B) * r[t];
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double tr = __dadd_rd(fy[t], PMVS_MAGIC_FLOOR);
+                    px[t] = __double2int_rd(ix[t]);
+                    q[t] = __ldg(quad + (__double2loint(tr) * cols + px[t]));
+                    fy[t] = fy[t] - (tr - PMVS_MAGIC_FLOOR);
+                }
+                double col[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int ndx = dp4a_us(q[t], 0x0000ff01, 0), ndxy = dp4a_us(q[t], (int)0xff0101ffu, 0), idy = dp4a_us(q[t], 0x000100ff, 0);
+                    const int g00 = (int)(q[t] & 0xffu);
+                    const int k0 = px[t] * ndx + g00, k1 = px[t] * ndxy + idy;
+                    col[t] = fma(fy[t], fma(-ix[t], (double)ndxy, (double)k1), fma(-ix[t], (double)ndx, (double)k0));
+                }
+#pragma unroll
+                for (int t = 1; t < 4; ++t) col[t] = shfl_xor_f64(col[t], t);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (4 * c + (s ^ t) >= NG) col[t] = 0.0;
+                sum += (col[0] + col[1]) + (col[2] + col[3]);
+                sts_f64x2(stA + 1024u * (unsigned)c, col[0], col[1]);
+                sts_f64x2(stA + 1024u * (unsigned)c + 512u, col[2], col[3]);
+            }
+            const double cref = lds_f64(rcA + pix);
+            sum += cref;
+            const double mean = sum * invV;
+            double dev = 0;
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                const double2 a = lds_f64x2_v(stA + 1024u * (unsigned)c), b = lds_f64x2_v(stA + 1024u * (unsigned)c + 512u);
+                double d0 = fabs(a.x - mean), d1 = fabs(a.y - mean), d2 = fabs(b.x - mean), d3 = fabs(b.y - mean);
+                if (4 * c + 4 > NG) {                                        /* last chunk: padding views do not count */
+                    if (4 * c + (s ^ 0) >= NG) d0 = 0.0;
+                    if (4 * c + (s ^ 1) >= NG) d1 = 0.0;
+                    if (4 * c + (s ^ 2) >= NG) d2 = 0.0;
+                    if (4 * c + (s ^ 3) >= NG) d3 = 0.0;
+                }
+                dev += (d0 + d1) + (d2 + d3);
+            }
+            dev += fabs(cref - mean);
+            double wgt;
+            if (GRAD) wgt = lds_f64(pwA + pix);                                              /* patch.cpp:1030-1032, :1036-1038, :986 */
+            else {
+                wgt = 0.0;
+                if (mlo & 1u) wgt = lds_f64(ya[0] + jo + 8u);
+                mlo >>= 1;
+            }
+            wgt *= exp_table_c(dev * dev * negK, tabA);                                      /* patch.cpp:1033-1035 */
+            csw += wgt;
+            cfit = fma(wgt, dev, cfit);
+            pix += 32u;
+        }
+        sw = fma(gxv, csw, sw);
+        fit = fma(gxv, cfit, fit);
+    }
+    fitOut = warp_sum(fit) * invV;
+    swOut = warp_sum(sw);
+}
+
+/*
+ * Many views without a colour stash (fitness_vl_rows): a quad of lanes owns one window pixel at a time (8 columns per pass,
+ * rows one after the other); lane s samples the views {4c + s} — at most 4 G4 of them — and keeps THEIR colours in
+ * registers. The cross-view sum and the sum of absolute deviations are quad all-reduces (two butterfly shuffles each; the
+ * pairwise order (l0 + l1) + (l2 + l3) is the same on every lane), so nothing has to be transposed or stored, one sampling
+ * pass, and the shared memory stays what the scene's tables need (two CTAs per SM at 64 views). The per-pixel tail
+ * (weights, accumulation) is computed by all four lanes and accumulated by lane 0 of the quad: for V >= 10 it is a few
+ * per cent of the pixel's work.
+ */
+template <int GLN, int G4, bool GRAD>
+__device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *__restrict__ Hw,
+                                             const double *__restrict__ sExpT, double &fitOut, double &swOut) {
+    constexpr int NV = 4 * G4;                       /* views of one lane */
+    constexpr int LGN = GLN == 4 ? 2 : (GLN == 2 ? 1 : 0);
+    const int lane = threadIdx.x & 31, s = lane & (GLN - 1), ci = lane >> LGN;
+    const int V = E.V, NG = V - 1, refV = E.refView, nx = R.nx, ny = R.ny, nyp = R.nyp;
+    const unsigned hA = smem_addr(Hw), xsA = smem_addr(R.xs), gxA = smem_addr(R.gx), ysgA = smem_addr(R.ysg), mkA = smem_addr(R.mask);
+    const unsigned rcA = smem_addr(R.refc), pwA = GRAD ? smem_addr(R.pw) : 0u, tabA = smem_addr(sExpT), viewA = smem_addr(E.view);
+    const double invV = 1.0 / (double)V;
+    const double negK = S.cfg.adaptiveDifferenceEnable ? -(invV * invV) / S.cfg.diffWeighting : 0.0;
+    /* this lane's views are {4n + s}: table addresses (homography row, view record) are formed per sample — arrays of them
+     * would cost 2 registers per view; padding entries (4n + s >= NG) sample view 0 again and are masked out */
+    const int nReal = NG > s ? (NG - s + GLN - 1) >> LGN : 0;   /* n < nReal  <=>  GLN n + s < NG */
+    const bool never = S.cfg.patchRadius < 0;
+    double fit = 0, sw = 0;
+    for (int i0 = 0; i0 < nx; i0 += 32 / GLN) {
+        const int i = i0 + ci;
+        const bool colOk = i < nx;
+        const int ic = colOk ? i : nx - 1;
+        const double x = lds_f64(xsA + 8u * ic);
+        const double gxv = (colOk && s == 0) ? (GRAD ? 1.0 : lds_f64(gxA + 8u * ic)) : 0.0;      /* lane 0 of the quad accumulates */
+        const unsigned long long mk = GRAD ? 0ull : lds_u64(mkA + 8u * ic);
+        double cfit = 0, csw = 0;
+        for (int j = 0; j < ny; ++j) {
+            const double y = lds_f64(ysgA + 16u * j);
+            double col[NV];
+#pragma unroll
+            for (int g = 0; g < G4; ++g) {
+                double w[4], r[4], e[4], ix[4], fy[4];
+                int px[4];
+                uint32_t q[4];
+                unsigned hv[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int n = 4 * g + t;
+                    const int k = n < nReal ? GLN * n + s : 0;
+                    hv[t] = (unsigned)(k + (k >= refV ? 1 : 0));     /* view index (the reference view is skipped) */
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const unsigned h = hA + 72u * hv[t];
+                    w[t] = fma(lds_f64_v(h + 56u), y, fma(lds_f64_v(h + 48u), x, lds_f64_v(h + 64u)));      /* volatile: a plain load is row-invariant and would be hoisted out of the row loop into 9 registers per view */
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[t]) : "d"(w[t]));
+#pragma unroll
+                for (int t = 0; t < 4; ++t) e[t] = fma(-w[t], r[t], 1.0);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) e[t] = fma(e[t], e[t], e[t]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r[t] = fma(r[t], e[t], r[t]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const unsigned h = hA + 72u * hv[t];
+                    ix[t] = fma(lds_f64_v(h + 8u), y, fma(lds_f64_v(h), x, lds_f64_v(h + 16u))) * r[t];
+                    fy[t] = fma(lds_f64_v(h + 32u), y, fma(lds_f64_v(h + 24u), x, lds_f64_v(h + 40u))) * r[t];
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const unsigned va = viewA + (unsigned)sizeof(ViewS) * hv[t];
+                    const uint32_t *__restrict__ quad = (const uint32_t *)lds_u64(va + (unsigned)offsetof(ViewS, quad));
+                    const int cols = lds_s32(va + (unsigned)offsetof(ViewS, cols));
+                    const double tr = __dadd_rd(fy[t], PMVS_MAGIC_FLOOR);
+                    px[t] = __double2int_rd(ix[t]);
+                    q[t] = __ldg(quad + (__double2loint(tr) * cols + px[t]));
+                    fy[t] = fy[t] - (tr - PMVS_MAGIC_FLOOR);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int ndx = dp4a_us(q[t], 0x0000ff01, 0), ndxy = dp4a_us(q[t], (int)0xff0101ffu, 0), idy = dp4a_us(q[t], 0x000100ff, 0);
+                    const int g00 = (int)(q[t] & 0xffu);
+                    const int k0 = px[t] * ndx + g00, k1 = px[t] * ndxy + idy;
+                    const double cc = fma(fy[t], fma(-ix[t], (double)ndxy, (double)k1), fma(-ix[t], (double)ndx, (double)k0));
+                    col[4 * g + t] = (4 * g + t) < nReal ? cc : 0.0;
+                }
+                /* a never-taken branch = a basic-block boundary: ptxas would otherwise interleave all 4 G4 samples and spill */
+                if (G4 > 2 && never) col[4 * g] = -col[4 * g];
+            }
+            double sum = tree_sum<NV>(col);
+            if (GLN > 1) sum += shfl_xor_f64(sum, 1);
+            if (GLN > 2) sum += shfl_xor_f64(sum, 2);
+            const unsigned pix = 8u * (unsigned)(ic * nyp + j);
+            const double cref = lds_f64(rcA + pix);
+            sum += cref;
+            const double mean = sum * invV;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) col[n] = n < nReal ? fabs(col[n] - mean) : 0.0;
+            double dev = tree_sum<NV>(col);
+            if (GLN > 1) dev += shfl_xor_f64(dev, 1);
+            if (GLN > 2) dev += shfl_xor_f64(dev, 2);
+            dev += fabs(cref - mean);
+            double wgt;
+            if (GRAD) wgt = lds_f64(pwA + pix);                                              /* patch.cpp:1030-1032, :1036-1038, :986 */
+            else {
+                wgt = 0.0;
+                if ((mk >> (16 * (j & 3) + (j >> 2))) & 1ull) wgt = lds_f64(ysgA + 16u * j + 8u);
+            }
+            wgt *= exp_table_c(dev * dev * negK, tabA);                                      /* patch.cpp:1033-1035 */
+            csw += wgt;
+            cfit = fma(wgt, dev, cfit);
+        }
+        sw = fma(gxv, csw, sw);
+        fit = fma(gxv, cfit, fit);
+    }
+    fitOut = warp_sum(fit) * invV;
+    swOut = warp_sum(sw);
+}
+
 /* dispatch on the number of non-reference views NG = 1..8; false: not covered */
 __device__ __forceinline__ bool fitness_vl_dispatch(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *Hw, const double *sExpT,
-                                                    double &fit, double &sw) {
+                                                    double *stash, double &fit, double &sw) {
+    const int NGv = E.V - 1;
+    if (R.pw || NGv > PMVS_VL_VIEWS - 1) {    /* gradient weighting (per-pixel weights) or more views than the register form holds */
+#if PMVS_VL_MANY_STASH
+        if (stash) {
+            if (R.pw) fitness_vl_many<true>(S, E, R, Hw, sExpT, stash, fit, sw);
+            else fitness_vl_many<false>(S, E, R, Hw, sExpT, stash, fit, sw);
+            return true;
+        }
+#endif
+        /* lanes per pixel: few views -> fewer lanes share a pixel (the per-pixel tail is computed by all of them) */
+        const int forced = (S.useVL >> 4) & 7;
+        const int gln = forced ? forced : (NGv <= 16 ? 1 : (NGv <= 32 ? 2 : 4));
+#define PMVS_ROWS(GLN_, G4_) do { if (R.pw) fitness_vl_rows<GLN_, G4_, true>(S, E, R, Hw, sExpT, fit, sw); else fitness_vl_rows<GLN_, G4_, false>(S, E, R, Hw, sExpT, fit, sw); } while (0)
+        if (gln == 1) {
+            if (NGv <= 4) PMVS_ROWS(1, 1);
+            else if (NGv <= 8) PMVS_ROWS(1, 2);
+            else if (NGv <= 12) PMVS_ROWS(1, 3);
+            else if (NGv <= 16) PMVS_ROWS(1, 4);
+            else PMVS_ROWS(4, 4);
+        } else if (gln == 2) {
+            if (NGv <= 8) PMVS_ROWS(2, 1);
+            else if (NGv <= 16) PMVS_ROWS(2, 2);
+            else if (NGv <= 24) PMVS_ROWS(2, 3);
+            else if (NGv <= 32) PMVS_ROWS(2, 4);
+            else PMVS_ROWS(4, 4);
+        } else {
+            if (NGv <= 16) PMVS_ROWS(4, 1);
+            else if (NGv <= 32) PMVS_ROWS(4, 2);
+            else if (NGv <= 48) PMVS_ROWS(4, 3);
+            else PMVS_ROWS(4, 4);
+        }
+#undef PMVS_ROWS
+        return true;
+    }
     switch (E.V - 1) {
     case 1: fitness_vl<1, 1, 8, true>(S, E, R, Hw, sExpT, fit, sw); return true;
     case 2: fitness_vl<2, 1, 4, true>(S, E, R, Hw, sExpT, fit, sw); return true;
@@ -1304,11 +1604,9 @@ __device__ __forceinline__ bool fitness_vl_dispatch(const DevScene &S, const Eva
     default: return false;
     }
 }
-/* configurations the view-lane loop covers: no gradient weight (it would need a per-pixel table of the reference edge
- * term), difference-weight exponent provably in [-700, 0] (|deviation| <= 255 per view) */
+/* configurations the view-lane loop covers: difference-weight exponent provably in [-700, 0] (|deviation| <= 255 per view) */
 __device__ __forceinline__ bool vl_config_ok(const DevScene &S) {
-    return S.useVL && !S.cfg.adaptiveGradientEnable &&
-           (!S.cfg.adaptiveDifferenceEnable || -(255.0 * 255.0) / S.cfg.diffWeighting >= -700.0);
+    return S.useVL && (!S.cfg.adaptiveDifferenceEnable || -(255.0 * 255.0) / S.cfg.diffWeighting >= -700.0);
 }
 
 /*
@@ -1328,7 +1626,8 @@ __device__ __forceinline__ void build_ref_win(const DevScene &S, const EvalCtx &
     if (tid == 0) {
         R.ok = 0;
         R.nx = R.ny = 0;
-        if (E.valid && E.refView >= 0 && E.V >= 2 && E.V <= 9 && vl_config_ok(S)) {
+        if (E.valid && E.refView >= 0 && E.V >= 2 && E.V <= PMVS_MAX_VIEWS && vl_config_ok(S) &&
+            (!S.cfg.adaptiveGradientEnable || (R.pw != nullptr && E.refEdge != nullptr))) {
             double pt[2];
             const double c[3] = {center[0], center[1], center[2]};
             if (ref_window_ok(S, E, c, pt)) {
@@ -1382,7 +1681,18 @@ __device__ __forceinline__ void build_ref_win(const DevScene &S, const EvalCtx &
         const double c = ref_sample(rc, make_int2(py * refCols, 2 * (__double2int_rn(y) - py)), y - (ty - PMVS_MAGIC_FLOOR), keep);
         R.refc[i * R.nyp + j] = c;
         if (keep) atomicOr(R.mask + i, 1ull << (fw * (j & (gl - 1)) + j / gl));
+        if (R.pw) {      /* distance x gradient weight of this pixel, zero on background (patch.cpp:1030-1032, :1036-1038, :986) */
+            const size_t rofs = (size_t)__double2int_rn(y) * refCols + __double2int_rn(x);
+            double wgt = R.gx[i] * R.ysg[j].y;
+            wgt *= exp(-1.0 / (__ldg(E.refEdge + rofs) * S.cfg.gradientWeighting));
+            R.pw[i * R.nyp + j] = keep ? wgt : 0.0;
+        }
     }
+    if (R.pw)
+        for (int idx = tid; idx < nx * (nyPad - ny); idx += nthreads) {
+            const int i = idx / (nyPad - ny), j = ny + idx % (nyPad - ny);
+            R.pw[i * R.nyp + j] = 0.0;
+        }
     ref_win_sync<WARP>();
 }
 
@@ -1448,9 +1758,9 @@ __device__ __noinline__ double warp_window(const DevScene &S, const EvalCtx &E, 
     if (inside) {
         ok = true;
         /* lane-per-column loop: every V in 2..16 has its own instantiation, reached from the VCAP = 8 / 16 entry */
-        if (VCAP == 8 && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
-        else if (VCAP == 16 && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
-        else if (VCAP == 0 && nx > 0 && E.refView >= 0) fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
+        if (VCAP == 8 && W.gv && nx > 0 && E.refView >= 0 && fitness_columns_dispatch<8>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
+        else if (VCAP == 16 && W.gv && nx > 0 && E.refView >= 0 && E.V > 8 && fitness_columns_dispatch<16>(E.V, S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw)) {}
+        else if (VCAP == 0 && W.gv && nx > 0 && E.refView >= 0) fitness_columns_many(S, E, sDistW, sDistW + PMVS_DIST_PAD(ps), W, nx, ny, fit, sw);
         else ok = fitness_samples<VCAP, false>(S, E, sDistW, W.H, W.xs, W.ys, nx, ny, fit, sw);
     } else {
         /* Exact early-out. The four window corners are window samples: if the reference pixel of one is not masked
@@ -1496,7 +1806,7 @@ __device__ __noinline__ bool warp_window_vl(const DevScene &S, const EvalCtx &E,
     }
     if (!__all_sync(PMVS_FULL, inside)) return false;
     double fit, sw;
-    if (!fitness_vl_dispatch(S, E, R, W.H, sExpT, fit, sw)) return false;
+    if (!fitness_vl_dispatch(S, E, R, W.H, sExpT, W.stash, fit, sw)) return false;
     __syncwarp();
     result = fit / sw;                                                                /* patch.cpp:1046 */
     return true;

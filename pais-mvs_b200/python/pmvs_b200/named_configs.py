@@ -2,7 +2,7 @@
 configs[3] and [4] keep the named view count, patch radius, weights and swarm but may be built on a reduced image size
 (`scale`) where a test has to synthesise them on the host in seconds (the work of one evaluation, O(V (2r+1)^2), does not
 depend on the image size: SURVEY.md section 5)."""
-from pmvs_b200 import abi, scene
+from . import abi, scene
 
 CONFIGS = {
     1: dict(name="configs[0]: 5 views 640x480, patchRadius=7, 1 pyramid level, adaptive weights off", views=5, w=640, h=480, r=7, levels=1,

@@ -67,7 +67,7 @@ def camera_max_lod(cols, rows, cfg):
 def resize_area(img, f):
     """cv::resize(img, Size(), f, f, INTER_AREA) (camera.cpp:85) — by OpenCV itself: the synthetic scenes are built with the
     library the reference uses (cv2 here is 4.x; its INTER_AREA code path is the 2.4 one). The restatement the device
-    kernels are checked against lives with the test infrastructure (oracle/orc_pyramid.py)."""
+    kernels are checked against lives with the test infrastructure, not in this package."""
     import cv2
     return cv2.resize(np.ascontiguousarray(img), None, fx=f, fy=f, interpolation=cv2.INTER_AREA)
 

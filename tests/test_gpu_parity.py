@@ -18,7 +18,7 @@ import os
 import numpy as np
 import pytest
 
-import named_configs
+from pmvs_b200 import named_configs
 import orc
 import refine_cases
 from pmvs_b200 import abi, scene

@@ -16,7 +16,7 @@ from pmvs_b200 import abi, scene  # noqa: E402
 from pmvs_b200.api import PatchRefiner  # noqa: E402
 from test_gpu_parity import compare_refine  # noqa: E402
 
-from named_configs import CONFIGS  # noqa: E402
+from pmvs_b200.named_configs import CONFIGS  # noqa: E402
 
 
 def run(k):
