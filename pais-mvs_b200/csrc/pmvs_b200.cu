@@ -435,6 +435,7 @@ struct pmvs_ctx {
     size_t scratchStride = 0;
     int scratchCtas = 0;
     int *dCounter = nullptr;
+    int *dDbgFoot = nullptr;             /* experiment builds only (PMVS_FOOTPRINT) */
     cudaEvent_t lastLaunch = nullptr;    /* refine launches of one context share its work counters and scratch slabs: they are serialised */
     void *dIn = nullptr, *dOut = nullptr;
     size_t dInBytes = 0, dOutBytes = 0;
@@ -514,6 +515,12 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     s.cams = ctx->dCams;
     s.distW = ctx->dDistW;
     s.distG = ctx->dDistW + w.size();
+    s.dbgFoot = nullptr;
+#if PMVS_FOOTPRINT
+    if (!ctx->dDbgFoot) CK(cudaMalloc(&ctx->dDbgFoot, sizeof(int) * 65536 * 32));
+    CK(cudaMemset(ctx->dDbgFoot, 0, sizeof(int) * 65536 * 32));
+    s.dbgFoot = ctx->dDbgFoot;
+#endif
     s.nCams = ctx->nCams;
     s.seed = ctx->seed;
     {
@@ -947,6 +954,17 @@ int pmvs_refine_batch_device(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, Pmvs
     CK(cudaSetDevice(ctx->device));
     return refine_launch(ctx, n, d_in, d_out, flags, cudaStream ? (cudaStream_t)cudaStream : ctx->stream);
 }
+
+#if PMVS_FOOTPRINT
+/* experiment builds only: bounding boxes {x0, y0, x1, y1} per patch and view (8 views) of the first swarm's evaluated windows */
+int pmvs_debug_footprints(pmvs_ctx *ctx, int n, int *out) {
+    if (!ctx || !ctx->dDbgFoot || n > 65536) return PMVS_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, ctx->dDbgFoot, sizeof(int) * (size_t)n * 32, cudaMemcpyDeviceToHost));
+    return PMVS_OK;
+}
+#endif
 
 int pmvs_pack_records_device(pmvs_ctx *ctx, int n, const PmvsPatchOut *d_out, double *d_records, uint64_t *d_counters, void *cudaStream) {
     if (!ctx || ctx->device < 0) return PMVS_E_ARG;

@@ -82,6 +82,7 @@ struct DevScene {
     const DevCamera *cams;
     const double *distW;       /* patchSize^2, index x*patchSize+y (mvs.cpp:104-109) */
     const double *distG;       /* patchSize: distW[x][y] = distG[x] * distG[y] up to rounding (the Gaussian is separable) */
+    int *dbgFoot;              /* experiment builds (PMVS_FOOTPRINT): per patch 8 views x 4 ints, else nullptr */
     double *scratch;           /* per-CTA correlation windows: scratchStride doubles per CTA */
     unsigned long long scratchStride;
     int nCams, useVL;          /* useVL: the view-lane window loop (fitness_vl) is enabled */
@@ -112,6 +113,14 @@ struct EvalCtx {
  * canonical pt take the per-hypothesis path).
  */
 #define PMVS_PT_TOL 1e-9
+#ifndef PMVS_TILE
+#define PMVS_TILE 0             /* T > 0: experiment build that stages a T x T quad tile per non-reference view in shared memory with
+                                   cp.async.bulk + mbarrier (the TMA unit) once per swarm and reads the taps of every evaluation that stays
+                                   inside the tiles from it (profiles/r2_tile_staging.md) */
+#endif
+#ifndef PMVS_FOOTPRINT
+#define PMVS_FOOTPRINT 0        /* 1: experiment build that records the image footprint of every swarm (tools/footprints.py) */
+#endif
 #define PMVS_PS_PAD8(ps) (((ps) + 7) & ~7)          /* window rows incl. the padding rows of the view-lane loop's trips */
 #define PMVS_NYP(ps) (((PMVS_PS_PAD8(ps) + 11) & ~15) + 4)     /* row pitch of the colour table: = 4 (mod 16) doubles: conflict-free quads */
 struct RefWin {
@@ -124,9 +133,20 @@ struct RefWin {
     double *pw;                  /* gradient weighting on: nx x nyp per-pixel weights = distance weight x gradient weight
                                     (patch.cpp:1030-1032, :1036-1038) x background mask; nullptr otherwise */
     int nx, ny, nyp, ok, gl, _pad;
+#if PMVS_TILE
+    uint32_t *tile;              /* experiment build: 4 quad tiles of PMVS_TILE x PMVS_TILE words, one per non-reference view */
+    int tox[4], toy[4];          /* tile origins in the views' level images */
+    unsigned long long mbar;     /* mbarrier of the bulk copies */
+    int tileOk, tilePhase;
+#endif
+#if PMVS_FOOTPRINT
+    int foot[8][4];              /* experiment build: per view, bounding box {x0, y0, x1, y1} of every window the swarm evaluated */
+    int footc[8][2];             /* per view: centre of the first window evaluated (the tile a per-patch staging would be centred on) */
+    int footn[8];                /* evaluations: all, inside a 48 / 64 / 96 / 128 pixel tile around footc in EVERY view; [5] = centre set */
+#endif
 };
 /* doubles one RefWin's tables take for patch size ps: xs | gx | ysg | mask | refc | pw */
-#define PMVS_REFWIN_DOUBLES(ps, grad) (5 * (size_t)PMVS_PS_PAD8(ps) + (size_t)(ps) * PMVS_NYP(ps) * ((grad) ? 2 : 1))
+#define PMVS_REFWIN_DOUBLES(ps, grad) (5 * (size_t)PMVS_PS_PAD8(ps) + (size_t)(ps) * PMVS_NYP(ps) * ((grad) ? 2 : 1) + (size_t)(4 * PMVS_TILE * PMVS_TILE / 2))
 __device__ __forceinline__ void carve_ref_win(RefWin &R, double *base, int ps, bool grad) {
     const int pp = PMVS_PS_PAD8(ps);
     R.xs = base;
@@ -135,6 +155,11 @@ __device__ __forceinline__ void carve_ref_win(RefWin &R, double *base, int ps, b
     R.mask = (unsigned long long *)(base + 4 * pp);
     R.refc = base + 5 * pp;
     R.pw = grad ? R.refc + (size_t)ps * PMVS_NYP(ps) : nullptr;
+#if PMVS_TILE
+    R.tile = (uint32_t *)(R.refc + (size_t)ps * PMVS_NYP(ps) * (grad ? 2 : 1));     /* 16-byte aligned: every table before it is a multiple of 16 bytes */
+    R.tileOk = 0;
+    R.tilePhase = -1;
+#endif
     R.nyp = PMVS_NYP(ps);
     R.nx = R.ny = 0;
     R.ok = 0;
@@ -1063,7 +1088,7 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {      /* sum o
 #define PMVS_VL_PIPE 0          /* 1: software-pipelined trips (tap loads of trip t+1 issued before the pixel phase of trip t) */
 #endif
 
-template <int GL, int NCH, int RB, bool FULL>
+template <int GL, int NCH, int RB, bool FULL, bool TILE = false>
 __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *__restrict__ Hw,
                                         const double *__restrict__ sExpT, double &fitOut, double &swOut) {
     constexpr int CP = 32 / GL;                     /* columns per pass */
@@ -1098,6 +1123,15 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
         quad[c] = (const uint32_t *)lds_u64(va + (unsigned)offsetof(ViewS, quad));
         cols[c] = lds_s32(va + (unsigned)offsetof(ViewS, cols));
     }
+#if PMVS_TILE
+    unsigned tb[NCH];                /* TILE: shared address of tile word (0, 0) of this lane's view, origin folded in */
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        int k = c * GL + s;
+        if (k >= NG || k >= 4) k = 0;
+        tb[c] = smem_addr(R.tile) + 4u * (unsigned)(k * PMVS_TILE * PMVS_TILE) - 4u * (unsigned)(R.toy[k] * PMVS_TILE + R.tox[k]);
+    }
+#endif
     /* which of the views that reach this lane in the pixel phase are real (padding views excluded) */
     bool real[NCH][GL];
 #pragma unroll
@@ -1158,6 +1192,10 @@ __device__ __noinline__ void fitness_vl(const DevScene &S, const EvalCtx &E, con
             tp.px[n] = __double2int_rd(tp.ix[n]);          /* floor on the conversion unit (F2I.F64.FLOOR): the FP64 / integer dispatch is the loop's bound */
 #else
             tp.px[n] = __double2loint(w[n]);
+#endif
+#if PMVS_TILE
+            if (TILE) tp.q[n] = (uint32_t)lds_s32(tb[n / (GL * RB)] + 4u * (unsigned)(__double2loint(r[n]) * PMVS_TILE + tp.px[n]));
+            else
 #endif
             tp.q[n] = __ldg(quad[n / (GL * RB)] + (__double2loint(r[n]) * cols[n / (GL * RB)] + tp.px[n]));
         }
@@ -1557,9 +1595,63 @@ __device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E
     swOut = warp_sum(sw);
 }
 
+#if PMVS_TILE
+/* Stage the tiles of the current swarm (CTA-collective; warp 0's homography area Hc is free before the swarm starts):
+ * origins from the canonical hypothesis' window centre in each view, rows copied by cp.async.bulk (one bulk copy of
+ * 4 T bytes per tile row, the TMA unit), completion on one mbarrier. */
+__device__ __forceinline__ void stage_tiles(const DevScene &S, const EvalCtx &E, RefWin &R, const double *center, const double *normal, double *Hc) {
+    const int tid = threadIdx.x, T = PMVS_TILE;
+    if (tid == 0) R.tileOk = 0;
+    if (!R.ok || E.V != 5 || E.refView < 0) { __syncthreads(); return; }
+    if (tid < 32) {
+        warp_homographies(E, center, normal, Hc);
+        if (tid < 4) {
+            const int v = tid + (tid >= E.refView ? 1 : 0);
+            const double *H = Hc + 9 * v;
+            const double x = R.pt[0], y = R.pt[1];
+            const double w = H[6] * x + H[7] * y + H[8];
+            int ox = ((int)floor((H[0] * x + H[1] * y + H[2]) / w) - T / 2) & ~3, oy = (int)floor((H[3] * x + H[4] * y + H[5]) / w) - T / 2;
+            const ViewS &vw = E.view[v];
+            ox = ox < 0 ? 0 : (ox > ((vw.cols - T) & ~3) ? ((vw.cols - T) & ~3) : ox);
+            oy = oy < 0 ? 0 : (oy > vw.rows - T ? vw.rows - T : oy);
+            R.tox[tid] = ox;
+            R.toy[tid] = oy;
+            if (vw.cols < T + 4 || vw.rows < T || (vw.cols & 3)) atomicExch(&R.tileOk, -1);      /* bulk copies need 16-byte aligned rows */
+        }
+    }
+    __syncthreads();
+    if (R.tileOk < 0) { if (tid == 0) R.tileOk = 0; __syncthreads(); return; }
+    const unsigned mbar = smem_addr(&R.mbar);
+    if (tid == 0) {
+        if (R.tilePhase < 0) {       /* first use by this CTA */
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+            R.tilePhase = 0;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       /* earlier generic-proxy reads of the tiles / the init before the async writes */
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(4 * T * T * 4) : "memory");
+    }
+    __syncthreads();
+    for (int r = tid; r < 4 * T; r += blockDim.x) {
+        const int k = r / T, row = r - k * T, v = k + (k >= E.refView ? 1 : 0);
+        const ViewS &vw = E.view[v];
+        const uint32_t *src = vw.quad + ((size_t)(R.toy[k] + row) * vw.cols + R.tox[k]);
+        const unsigned dst = smem_addr(R.tile) + 4u * (unsigned)(k * T * T + row * T);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(4 * T), "r"(mbar)
+                     : "memory");
+    }
+    const int parity = R.tilePhase & 1;
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    __syncthreads();
+    if (tid == 0) { R.tilePhase ^= 1; R.tileOk = 1; }
+    __syncthreads();
+}
+#endif
+
 /* dispatch on the number of non-reference views NG = 1..8; false: not covered */
 __device__ __forceinline__ bool fitness_vl_dispatch(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *Hw, const double *sExpT,
-                                                    double *stash, double &fit, double &sw) {
+                                                    double *stash, double &fit, double &sw, bool tileHit = false) {
     const int NGv = E.V - 1;
     if (R.pw || NGv > PMVS_VL_VIEWS - 1) {    /* gradient weighting (per-pixel weights) or more views than the register form holds */
 #if PMVS_VL_MANY_STASH
@@ -1598,7 +1690,11 @@ __device__ __forceinline__ bool fitness_vl_dispatch(const DevScene &S, const Eva
     case 1: fitness_vl<1, 1, 8, true>(S, E, R, Hw, sExpT, fit, sw); return true;
     case 2: fitness_vl<2, 1, 4, true>(S, E, R, Hw, sExpT, fit, sw); return true;
     case 3: fitness_vl<4, 1, PMVS_VL_RB, false>(S, E, R, Hw, sExpT, fit, sw); return true;
-    case 4: fitness_vl<4, 1, PMVS_VL_RB, true>(S, E, R, Hw, sExpT, fit, sw); return true;
+    case 4:
+#if PMVS_TILE
+        if (tileHit) { fitness_vl<4, 1, PMVS_VL_RB, true, true>(S, E, R, Hw, sExpT, fit, sw); return true; }
+#endif
+        fitness_vl<4, 1, PMVS_VL_RB, true>(S, E, R, Hw, sExpT, fit, sw); return true;
     case 5: case 6: case 7: fitness_vl<4, 2, 1, false>(S, E, R, Hw, sExpT, fit, sw); return true;
     case 8: fitness_vl<4, 2, 1, true>(S, E, R, Hw, sExpT, fit, sw); return true;
     default: return false;
@@ -1805,8 +1901,79 @@ __device__ __noinline__ bool warp_window_vl(const DevScene &S, const EvalCtx &E,
         if (!(w > 0.0 && nxw >= loX * w && nxw < hiX * w && nyw >= loY * w && nyw < hiY * w)) inside = false;
     }
     if (!__all_sync(PMVS_FULL, inside)) return false;
+#if PMVS_FOOTPRINT
+    if (E.V <= 8) {
+        RefWin &Rw = const_cast<RefWin &>(R);
+        for (int t = lane; t < 4 * E.V; t += 32) {
+            const int v = t >> 2, cidx = t & 3;
+            const double *H = W.H + 9 * v;
+            const double x = R.xs[(cidx & 1) ? nx - 1 : 0], y = R.ysg[(cidx & 2) ? ny - 1 : 0].x;
+            const double w = H[6] * x + H[7] * y + H[8];
+            const int px = (int)floor((H[0] * x + H[1] * y + H[2]) / w), py = (int)floor((H[3] * x + H[4] * y + H[5]) / w);
+            atomicMin(&Rw.foot[v][0], px);
+            atomicMin(&Rw.foot[v][1], py);
+            atomicMax(&Rw.foot[v][2], px + 1);
+            atomicMax(&Rw.foot[v][3], py + 1);
+        }
+        __syncwarp();
+        /* first evaluation of the swarm defines the tile centres */
+        int first = 0;
+        if (lane == 0) first = atomicCAS(&Rw.footn[5], 0, 1) == 0;
+        first = __shfl_sync(PMVS_FULL, first, 0);
+        int cxs = 0, cys = 0;
+        {
+            const int v = lane < E.V ? lane : 0;
+            const double *H = W.H + 9 * v;
+            const double x = R.xs[nx / 2], y = R.ysg[ny / 2].x;
+            const double w = H[6] * x + H[7] * y + H[8];
+            cxs = (int)floor((H[0] * x + H[1] * y + H[2]) / w);
+            cys = (int)floor((H[3] * x + H[4] * y + H[5]) / w);
+            if (first && lane < E.V) { Rw.footc[lane][0] = cxs; Rw.footc[lane][1] = cys; atomicExch(&Rw.footn[6], 1); }
+        }
+        if (first) __threadfence_block();
+        __syncwarp();
+        if (*(volatile int *)&Rw.footn[6]) {
+            bool in48 = true, in64 = true, in96 = true, in128 = true;
+            for (int t = lane; t < 4 * E.V; t += 32) {
+                const int v = t >> 2, cidx = t & 3;
+                const double *H = W.H + 9 * v;
+                const double x = R.xs[(cidx & 1) ? nx - 1 : 0], y = R.ysg[(cidx & 2) ? ny - 1 : 0].x;
+                const double w = H[6] * x + H[7] * y + H[8];
+                const int px = (int)floor((H[0] * x + H[1] * y + H[2]) / w), py = (int)floor((H[3] * x + H[4] * y + H[5]) / w);
+                const int dx = px - *(volatile int *)&Rw.footc[v][0], dy = py - *(volatile int *)&Rw.footc[v][1];
+                const int m = max(max(dx, -dx - 1), max(dy, -dy - 1)) + 1;      /* half-size needed incl. the +1 tap */
+                in48 = in48 && m <= 24; in64 = in64 && m <= 32; in96 = in96 && m <= 48; in128 = in128 && m <= 64;
+            }
+            in48 = __all_sync(PMVS_FULL, in48); in64 = __all_sync(PMVS_FULL, in64); in96 = __all_sync(PMVS_FULL, in96); in128 = __all_sync(PMVS_FULL, in128);
+            if (lane == 0) {
+                atomicAdd(&Rw.footn[0], 1);
+                if (in48) atomicAdd(&Rw.footn[1], 1);
+                if (in64) atomicAdd(&Rw.footn[2], 1);
+                if (in96) atomicAdd(&Rw.footn[3], 1);
+                if (in128) atomicAdd(&Rw.footn[4], 1);
+            }
+        }
+    }
+#endif
+    bool tileHit = false;
+#if PMVS_TILE
+    if (R.tileOk && E.V == 5) {          /* every window corner of every non-reference view inside that view's tile */
+        bool in = true;
+        for (int t = lane; t < 4 * E.V; t += 32) {
+            const int v = t >> 2, cidx = t & 3;
+            if (v == E.refView) continue;
+            const int k = v - (v > E.refView ? 1 : 0);
+            const double *H = W.H + 9 * v;
+            const double x = R.xs[(cidx & 1) ? nx - 1 : 0], y = R.ysg[(cidx & 2) ? ny - 1 : 0].x;
+            const double w = H[6] * x + H[7] * y + H[8];
+            const double ix = (H[0] * x + H[1] * y + H[2]) / w - R.tox[k], iy = (H[3] * x + H[4] * y + H[5]) / w - R.toy[k];
+            if (!(ix >= 1.0 && ix < PMVS_TILE - 1.0 && iy >= 1.0 && iy < PMVS_TILE - 1.0)) in = false;
+        }
+        tileHit = __all_sync(PMVS_FULL, in);
+    }
+#endif
     double fit, sw;
-    if (!fitness_vl_dispatch(S, E, R, W.H, sExpT, W.stash, fit, sw)) return false;
+    if (!fitness_vl_dispatch(S, E, R, W.H, sExpT, W.stash, fit, sw, tileHit)) return false;
     __syncwarp();
     result = fit / sw;                                                                /* patch.cpp:1046 */
     return true;

@@ -385,6 +385,13 @@ __device__ inline void cta_pso_optimization(const DevScene &S, CtaS &c, const do
         /* canonical hypothesis centre = the initial particle's (patch.cpp:204, :944) */
         const double ctr[3] = {c.E.ray[0] * p.depth + c.E.refC[0], c.E.ray[1] * p.depth + c.E.refC[1], c.E.ray[2] * p.depth + c.E.refC[2]};
         build_ref_win<false>(S, c.E, c.rw, ctr, tid, blockDim.x);
+#if PMVS_TILE
+        stage_tiles(S, c.E, c.rw, ctr, p.normal, W.H);      /* only warp 0 touches it: its own homography area, free before the swarm starts */
+#endif
+#if PMVS_FOOTPRINT
+        if (tid < 8) { c.rw.foot[tid][0] = c.rw.foot[tid][1] = 1 << 30; c.rw.foot[tid][2] = c.rw.foot[tid][3] = -(1 << 30); c.rw.footn[tid] = 0; }
+        __syncthreads();
+#endif
     }
     __shared__ double sInit[3];
     if (tid == 0) {
@@ -422,6 +429,11 @@ __device__ inline void cta_pso_optimization(const DevScene &S, CtaS &c, const do
         p.psoIterations = c.pso.iteration;
         p.psoRuns++;
         p.evals += evals;
+#if PMVS_FOOTPRINT
+        if (S.dbgFoot && W.rw && p.psoRuns == 1 && c.nextIdx < 65536)
+            for (int v = 0; v < 8; ++v)
+                for (int k = 0; k < 4; ++k) S.dbgFoot[(c.nextIdx * 8 + v) * 4 + k] = v < c.E.V ? c.rw.foot[v][k] : (v == 7 ? c.rw.footn[k] : (v == 6 && k == 0 ? c.rw.footn[4] : 0));
+#endif
     }
     __syncthreads();
 }
