@@ -82,7 +82,7 @@ int main(int argc, char **argv) {
     int roundSize = 1024, device = 0, gpus = 1;
     unsigned long long seed = 42;
     double autosave = 5.0;
-    bool expand = true, verbose = false, mergeSlots = true;
+    bool expand = true, verbose = false, mergeSlots = true, pipeline = true;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if ((a == "-r" || a == "-f" || a == "-v" || a == "-a") && i + 1 < argc) { mode = a; input = argv[++i]; }
@@ -98,6 +98,7 @@ int main(int argc, char **argv) {
         else if (a == "--no-expand") expand = false;
         else if (a == "--merge-slots") mergeSlots = true;
         else if (a == "--slot-passes") mergeSlots = false;
+        else if (a == "--no-pipeline") pipeline = false;
         else if (a == "-V") verbose = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -126,6 +127,7 @@ int main(int argc, char **argv) {
     mvs.verbose = verbose;
     mvs.outDir = outDir;
     mvs.mergeSlots = mergeSlots;
+    mvs.pipelineRounds = pipeline;
     mvs.imageDir = imageDir;
 
     if (!loadAny(mvs, input)) { fprintf(stderr, "load failed: %s\n", mvs.lastError().c_str()); return 1; }

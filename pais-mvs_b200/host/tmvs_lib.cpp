@@ -540,18 +540,25 @@ bool MVS::ensureContext() {
         }
     }
     const std::chrono::steady_clock::time_point tc0 = std::chrono::steady_clock::now();
-    for (int g = 0; g < (numGpus > 0 ? numGpus : 1); ++g) {
-        pmvs_ctx *c = nullptr;
-        const int rc = pmvs_create(&c, &cfg, (int)recs.size(), recs.data(), device + g, rngSeed);
-        if (rc != PMVS_OK) {
-            err = std::string("pmvs_create (device ") + std::to_string(device + g) + "): " + (c ? pmvs_last_error(c) : "out of memory");
-            if (c) pmvs_destroy(c);
-            for (size_t k = 0; k < ctxs.size(); ++k) pmvs_destroy(ctxs[k]);
-            ctxs.clear();
+    /* one context per GPU, created side by side: each uploads the level-0 images and builds its own pyramids (seconds for many
+     * large images), so N GPUs cost one creation time, not N */
+    const int G = numGpus > 0 ? numGpus : 1;
+    std::vector<pmvs_ctx *> made(G, nullptr);
+    std::vector<int> rcs(G, PMVS_OK);
+    {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g)
+            th.emplace_back([&, g]() { rcs[g] = pmvs_create(&made[g], &cfg, (int)recs.size(), recs.data(), device + g, rngSeed); });
+        for (size_t k = 0; k < th.size(); ++k) th[k].join();
+    }
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != PMVS_OK) {
+            err = std::string("pmvs_create (device ") + std::to_string(device + g) + "): " + (made[g] ? pmvs_last_error(made[g]) : "out of memory");
+            for (int k = 0; k < G; ++k)
+                if (made[k]) pmvs_destroy(made[k]);
             return false;
         }
-        ctxs.push_back(c);
-    }
+    ctxs.assign(made.begin(), made.end());
     contextSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count();
     return true;
 }
@@ -576,6 +583,8 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
     const int n = (int)batch.size();
     std::vector<PmvsPatchIn> in(n);
     std::vector<PmvsPatchOut> out(n);
+    /* marshalling on all host cores: at 10^6 candidates per second the 1.3 KB result records are GB/s of memcpy */
+#pragma omp parallel for schedule(static) if (n >= 4096)
     for (int i = 0; i < n; ++i) {
         const Patch &p = *batch[i];
         PmvsPatchIn &r = in[i];
@@ -587,6 +596,7 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
         r.id = p.id;
         const std::vector<int> &cams = parentCams ? (*parentCams)[i] : p.camIdx;
         if (cams.size() > PMVS_MAX_VIEWS && !warnedViews) {
+#pragma omp critical
             warnedViews = true;
             fprintf(stderr, "tmvs: patch %d lists %zu cameras; only the first %d are used (PMVS_MAX_VIEWS)\n", p.id, cams.size(), PMVS_MAX_VIEWS);
         }
@@ -612,6 +622,8 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
     for (size_t g = 0; g < rcs.size(); ++g)
         if (rcs[g] != PMVS_OK) { err = std::string("pmvs_refine_batch: ") + (refineOverride ? "stand-in failed" : pmvs_last_error(ctxs[g])); return false; }
     refinedCount += n;
+    long sEv = 0, sWev = 0, sIt = 0, sRuns = 0, sDrop = 0, sViews = 0, sLOD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma omp parallel for schedule(static) reduction(+ : sEv, sWev, sIt, sRuns, sDrop, sViews, sLOD[:8]) if (n >= 4096)
     for (int i = 0; i < n; ++i) {
         Patch &p = *batch[i];
         const PmvsPatchOut &o = out[i];
@@ -624,18 +636,25 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
         p.LOD = o.LOD;
         p.refCamIdx = o.refCamIdx;
         p.drop = o.drop != 0;
-        statEvaluations += o.evaluations;
-        statWindowEvaluations += o.windowEvaluations;
-        statIterations += o.psoIterations;
-        statRuns += o.psoRuns;
-        statDropped += o.drop != 0;
-        statViews += o.nCam;
-        if (o.LOD >= 0 && o.LOD < 8) statLOD[o.LOD]++;
+        sEv += o.evaluations;
+        sWev += o.windowEvaluations;
+        sIt += o.psoIterations;
+        sRuns += o.psoRuns;
+        sDrop += o.drop != 0;
+        sViews += o.nCam;
+        if (o.LOD >= 0 && o.LOD < 8) sLOD[o.LOD]++;
         p.camIdx.assign(o.camIdx, o.camIdx + o.nCam);
         p.imgPoint.resize((size_t)o.nImgPoint * 2);
         for (int k = 0; k < o.nImgPoint; ++k) { p.imgPoint[2 * k] = o.imgPoint[k][0]; p.imgPoint[2 * k + 1] = o.imgPoint[k][1]; }
         if (o.nImgPoint > 0) patchColor(p);
     }
+    statEvaluations += sEv;
+    statWindowEvaluations += sWev;
+    statIterations += sIt;
+    statRuns += sRuns;
+    statDropped += sDrop;
+    statViews += sViews;
+    for (int l = 0; l < 8; ++l) statLOD[l] += sLOD[l];
     return true;
 }
 
@@ -689,26 +708,46 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
      * (slot, neighbour) combinations in the next round's pass, like the serial reference moves on to the next camera */
     struct Carry { int parent; std::vector<unsigned char> tried; };
     std::vector<Carry> carry;
-    for (int round = 0;; ++round) {
-        /* 1. pop up to roundSize parents in strategy order */
-        Clock::time_point tp0 = Clock::now();
+    /* One round's working set. Rounds are pipelined in the merged mode (below): while the GPUs refine round k's candidates the
+     * host already pops and generates round k+1 — from the state as of commit k-1 — and prunes it against commit k before it
+     * is launched (two half-rounds in flight, mvs.cpp:233-275 restructured). */
+    struct RoundWork {
         std::vector<int> parents;
         std::vector<std::vector<unsigned char> > tried;     /* per parent: (slot, neighbour) combinations already refined */
+        std::vector<int> nGenerated, nRejected, candParentIdx;
+        std::vector<Cand> cands;
+        std::vector<Patch> cpatch;
+        std::vector<std::vector<int> > parentCams;
+        size_t maxSlots = 0, nCands = 0, accepted = 0;
+    };
+    auto popParents = [&](RoundWork &W) {
+        /* 1. pop up to roundSize parents in strategy order */
+        Clock::time_point tp0 = Clock::now();
         for (size_t k = 0; k < carry.size(); ++k)
-            if (patches.find(carry[k].parent) != patches.end()) { parents.push_back(carry[k].parent); tried.push_back(carry[k].tried); }
+            if (patches.find(carry[k].parent) != patches.end()) { W.parents.push_back(carry[k].parent); W.tried.push_back(carry[k].tried); }
         carry.clear();
-        const size_t nCarried = parents.size();
-        while ((int)(parents.size() - nCarried) < roundSize) {
+        const size_t nCarried = W.parents.size();
+        while ((int)(W.parents.size() - nCarried) < roundSize) {
             const int id = getPatchIdFromQueue();
             if (id < 0) break;
             std::map<int, Patch>::iterator it = patches.find(id);
             if (it == patches.end()) continue;
             it->second.expanded = true;
             if (!runtimeFiltering(it->second)) { deletePatch(id); continue; }   /* mvs.cpp:255-260 */
-            parents.push_back(id);
+            W.parents.push_back(id);
         }
         tPop += std::chrono::duration<double>(Clock::now() - tp0).count();
-        if (parents.empty()) break;
+        if (W.parents.empty()) return;
+        W.maxSlots = 0;
+        for (size_t k = 0; k < W.parents.size(); ++k) {
+            std::map<int, Patch>::const_iterator pit = patches.find(W.parents[k]);
+            if (pit != patches.end()) W.maxSlots = std::max(W.maxSlots, pit->second.camIdx.size());
+        }
+        W.tried.resize(W.parents.size());
+        for (size_t k = 0; k < W.parents.size(); ++k) W.tried[k].resize(W.maxSlots * 4, 0);
+        W.nGenerated.assign(W.parents.size(), 0);
+        W.nRejected.assign(W.parents.size(), 0);
+    };
         /* 2.-4. The reference visits a parent's visible cameras one after the other (expandNeighborCell,
          * mvs.cpp:535-563) and inserts each refined candidate before looking at the next camera, so the (up to) five
          * views of the same 3-D neighbour are refined once: the first one fills the cells the others would target.
@@ -716,12 +755,6 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
          * --slot-passes: one pass per camera slot i — candidates of slot i for all parents -> GPU -> serial commit in
          * parent order -> slot i+1 sees the updated cell maps (the reference's visiting order; the passes of slots 1..
          * are sparse, each paying a full kernel latency). Default (mergeSlots): one pass, see below. */
-        size_t nCands = 0, accepted = 0;
-        size_t maxSlots = 0;
-        for (size_t k = 0; k < parents.size(); ++k) {
-            std::map<int, Patch>::const_iterator pit = patches.find(parents[k]);
-            if (pit != patches.end()) maxSlots = std::max(maxSlots, pit->second.camIdx.size());
-        }
         /* mergeSlots: ONE pass per round over all camera slots (slot-major, the order the per-slot passes commit in).
          * What the per-slot passes learn from the commits in between — "this cell now holds a neighbour of the parent"
          * (skipNeighborCell, mvs.cpp:803-804) — is predicted instead: a candidate is expected to land in the cells its
@@ -730,17 +763,14 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
          * the centre across a cell border, or the expected patch was rejected) cost a wasted refinement or leave a cell
          * to a later round; the commit below still re-checks every target cell against the real state. The sparse
          * passes of slots 1.. (tens of candidates, a full kernel latency each) disappear: 5x fewer, 5x larger calls. */
-        tried.resize(parents.size());
-        for (size_t k = 0; k < parents.size(); ++k) tried[k].resize(maxSlots * 4, 0);
-        std::vector<int> nGenerated(parents.size(), 0), nRejected(parents.size(), 0);
-        std::vector<int> candParentIdx;
-        for (size_t slot0 = 0; slot0 < maxSlots; slot0 = mergeSlots ? maxSlots : slot0 + 1) {
-            const size_t slot1 = mergeSlots ? maxSlots : slot0 + 1;
+    /* candidates of the camera slots [slot0, slot1) of W's parents; false: no parent has such a slot */
+    auto generate = [&](RoundWork &W, size_t slot0, size_t slot1) -> bool {
+        W.cands.clear();
+        W.cpatch.clear();
+        W.parentCams.clear();
+        W.candParentIdx.clear();
+        {
             Clock::time_point tg0 = Clock::now();
-            std::vector<Cand> cands;
-            candParentIdx.clear();
-            std::vector<Patch> cpatch;
-            std::vector<std::vector<int> > parentCams;
             /* a cell can take at most maxCellPatchNum patches (skipNeighborCell, mvs.cpp:794-795): do not refine more
              * candidates for a cell than it still has room for — the serial reference would have skipped them */
             ++passStamp;
@@ -755,10 +785,10 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
              * (skipNeighborCell, mvs.cpp:792-807: the patch look-ups and isNeighbor tests) — for every (parent, slot,
              * neighbour) on all host cores; the order-dependent part below stays serial */
             const size_t nSl = slot1 - slot0;
-            std::vector<unsigned char> open(parents.size() * nSl * 4, 0);
-#pragma omp parallel for schedule(dynamic, 32) if (parents.size() >= 128)
-            for (long k = 0; k < (long)parents.size(); ++k) {
-                std::map<int, Patch>::const_iterator pit = patches.find(parents[k]);
+            std::vector<unsigned char> open(W.parents.size() * nSl * 4, 0);
+#pragma omp parallel for schedule(dynamic, 32) if (W.parents.size() >= 128)
+            for (long k = 0; k < (long)W.parents.size(); ++k) {
+                std::map<int, Patch>::const_iterator pit = patches.find(W.parents[k]);
                 if (pit == patches.end()) continue;
                 const Patch &pth = pit->second;
                 for (size_t slot = slot0; slot < slot1; ++slot) {
@@ -772,8 +802,8 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             }
             bool anySlot = false;
             for (size_t slot = slot0; slot < slot1; ++slot)
-            for (size_t k = 0; k < parents.size(); ++k) {
-                std::map<int, Patch>::const_iterator pit = patches.find(parents[k]);
+            for (size_t k = 0; k < W.parents.size(); ++k) {
+                std::map<int, Patch>::const_iterator pit = patches.find(W.parents[k]);
                 if (pit == patches.end()) continue;
                 const Patch &pth = pit->second;
                 if (slot >= pth.camIdx.size() || 2 * slot + 1 >= pth.imgPoint.size()) continue;
@@ -784,14 +814,14 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
                 for (int j = 0; j < 4; ++j) {
                     if (!open[(k * nSl + (slot - slot0)) * 4 + j]) continue;
-                    if (tried[k][slot * 4 + j]) continue;
+                    if (W.tried[k][slot * 4 + j]) continue;
                     const size_t cellIdx = cellAt(ci, nx[j], ny[j]);
                     int &pend = scratch[ci].pend[cellIdx];
                     if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
                     if (mergeSlots) {
                         bool taken = false;
                         for (int q = scratch[ci].head[cellIdx]; q >= 0 && !taken; q = chain[q].second)
-                            taken = isNeighbor(pth, cpatch[chain[q].first], cfg.neighborRadius);
+                            taken = isNeighbor(pth, W.cpatch[chain[q].first], cfg.neighborRadius);
                         if (taken) continue;
                     }
                     ++pend;
@@ -801,13 +831,13 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                     getExpansionPatchCenter(cameras[ci], pth, nx[j], ny[j], e.center);
                     memcpy(e.normal, pth.normal, sizeof(e.normal));
                     normal2Spherical(e.normal, e.normalS);
-                    const Cand c = {parents[k], ci, nx[j], ny[j]};
-                    tried[k][slot * 4 + j] = 1;
-                    nGenerated[k]++;
-                    candParentIdx.push_back((int)k);
-                    cands.push_back(c);
-                    cpatch.push_back(e);
-                    parentCams.push_back(pth.camIdx);
+                    const Cand c = {W.parents[k], ci, nx[j], ny[j]};
+                    W.tried[k][slot * 4 + j] = 1;
+                    W.nGenerated[k]++;
+                    W.candParentIdx.push_back((int)k);
+                    W.cands.push_back(c);
+                    W.cpatch.push_back(e);
+                    W.parentCams.push_back(pth.camIdx);
                     if (mergeSlots)
                         for (size_t v = 0; v < pth.camIdx.size(); ++v) {
                             double pt[2];
@@ -816,39 +846,38 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                             const int ex = (int)(pt[0] / cfg.cellSize), ey = (int)(pt[1] / cfg.cellSize);
                             if (!cellMaps[cv].inMap(ex, ey)) continue;
                             const size_t eIdx = cellAt(cv, ex, ey);
-                            chain.push_back(std::make_pair((int)cpatch.size() - 1, scratch[cv].head[eIdx]));
+                            chain.push_back(std::make_pair((int)W.cpatch.size() - 1, scratch[cv].head[eIdx]));
                             scratch[cv].head[eIdx] = (int)chain.size() - 1;
                         }
                 }
             }
             tGen += std::chrono::duration<double>(Clock::now() - tg0).count();
-            if (!anySlot) break;
-            if (cands.empty()) continue;
-            ++gpuCalls;
-            refinedMax = std::max(refinedMax, (long)cands.size());
-            /* expandVisibleCamera + refine + removeInvisibleCamera on the GPU (mvs.cpp:572-574) */
-            std::vector<Patch *> batch(cpatch.size());
-            for (size_t k = 0; k < cpatch.size(); ++k) batch[k] = &cpatch[k];
-            if (!refineBatch(batch, PMVS_F_EXPAND_VISIBLE | PMVS_F_POST_REMOVE_INVISIBLE, &parentCams)) return false;
-            /* serial commit in parent order; the target cell is re-checked as the reference would have seen it */
+            return anySlot;
+        }
+    };
+    /* serial commit in parent order; the target cell is re-checked as the reference would have seen it */
+    auto commit = [&](RoundWork &W) {
+        {
             Clock::time_point tc0 = Clock::now();
-            for (size_t k = 0; k < cands.size(); ++k) {
-                std::map<int, Patch>::const_iterator pit = patches.find(cands[k].parent);
+            for (size_t k = 0; k < W.cands.size(); ++k) {
+                std::map<int, Patch>::const_iterator pit = patches.find(W.cands[k].parent);
                 if (pit == patches.end()) continue;
-                if (skipNeighborCell(cellMaps[cands[k].cam].cell(cands[k].cx, cands[k].cy), pit->second)) continue;
+                if (skipNeighborCell(cellMaps[W.cands[k].cam].cell(W.cands[k].cx, W.cands[k].cy), pit->second)) continue;
                 const size_t before = patches.size();
-                insertPatch(cpatch[k]);
-                accepted += patches.size() - before;
-                if (patches.size() == before) nRejected[candParentIdx[k]]++;      /* runtimeFiltering turned it down */
+                insertPatch(W.cpatch[k]);
+                W.accepted += patches.size() - before;
+                if (patches.size() == before) W.nRejected[W.candParentIdx[k]]++;      /* runtimeFiltering turned it down */
             }
-            nCands += cands.size();
+            W.nCands += W.cands.size();
             tCommit += std::chrono::duration<double>(Clock::now() - tc0).count();
         }
+    };
+    auto finishRound = [&](RoundWork &W, int round) {
         if (mergeSlots)
-            for (size_t k = 0; k < parents.size(); ++k)
-                if (nRejected[k] > 0 && nGenerated[k] > 0) { Carry c; c.parent = parents[k]; c.tried.swap(tried[k]); carry.push_back(c); }
+            for (size_t k = 0; k < W.parents.size(); ++k)
+                if (W.nRejected[k] > 0 && W.nGenerated[k] > 0) { Carry c; c.parent = W.parents[k]; c.tried.swap(W.tried[k]); carry.push_back(c); }
         if (verbose)
-            printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, parents.size(), nCands, accepted,
+            printf("round %d: parents %zu candidates %zu accepted %zu patches %zu queue %zu\n", round, W.parents.size(), W.nCands, W.accepted,
                    patches.size(), byPriorityQueueSize());
         /* mvs.cpp:265-268 checkpoints every 500 accepted patches; at GPU speed that is every few milliseconds and the
          * rewrite of the whole file becomes quadratic, so checkpoints are additionally spaced autosaveSeconds apart */
@@ -859,7 +888,73 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             writeMVS((outDir + "auto_save.mvs").c_str());
             tSave += std::chrono::duration<double>(Clock::now() - ts0).count();
         }
+    };
+    const unsigned refineFlags = PMVS_F_EXPAND_VISIBLE | PMVS_F_POST_REMOVE_INVISIBLE;     /* mvs.cpp:572-574 on the GPU */
+    if (mergeSlots && pipelineRounds) {
+        RoundWork cur;
+        popParents(cur);
+        if (!cur.parents.empty()) generate(cur, 0, cur.maxSlots);
+        for (int round = 0; !cur.parents.empty(); ++round) {
+            RoundWork next;
+            if (!cur.cands.empty()) {
+                ++gpuCalls;
+                refinedMax = std::max(refinedMax, (long)cur.cands.size());
+                std::vector<Patch *> batch(cur.cpatch.size());
+                for (size_t k = 0; k < cur.cpatch.size(); ++k) batch[k] = &cur.cpatch[k];
+                bool ok = true;
+                std::thread gpu([&]() { ok = refineBatch(batch, refineFlags, &cur.parentCams); });
+                /* meanwhile: the next round's parents and candidates, from the state before this round's commit */
+                popParents(next);
+                if (!next.parents.empty()) generate(next, 0, next.maxSlots);
+                gpu.join();
+                if (!ok) return false;
+                commit(cur);
+                /* prune what this commit closed: the parent is gone, or its target cell now skips (mvs.cpp:792-807) */
+                Clock::time_point tg0 = Clock::now();
+                size_t keep = 0;
+                for (size_t k = 0; k < next.cands.size(); ++k) {
+                    std::map<int, Patch>::const_iterator pit = patches.find(next.cands[k].parent);
+                    if (pit == patches.end() || skipNeighborCell(cellMaps[next.cands[k].cam].cell(next.cands[k].cx, next.cands[k].cy), pit->second)) continue;
+                    if (keep != k) {
+                        next.cands[keep] = next.cands[k];
+                        next.cpatch[keep] = next.cpatch[k];
+                        next.parentCams[keep].swap(next.parentCams[k]);
+                        next.candParentIdx[keep] = next.candParentIdx[k];
+                    }
+                    ++keep;
+                }
+                next.cands.resize(keep);
+                next.cpatch.resize(keep);
+                next.parentCams.resize(keep);
+                next.candParentIdx.resize(keep);
+                tGen += std::chrono::duration<double>(Clock::now() - tg0).count();
+            }
+            finishRound(cur, round);
+            if (next.parents.empty()) {             /* the queue was empty before this commit refilled it */
+                popParents(next);
+                if (!next.parents.empty()) generate(next, 0, next.maxSlots);
+            }
+            cur = std::move(next);
+        }
+    } else
+    for (int round = 0;; ++round) {
+        RoundWork W;
+        popParents(W);
+        if (W.parents.empty()) break;
+        for (size_t slot0 = 0; slot0 < W.maxSlots; slot0 = mergeSlots ? W.maxSlots : slot0 + 1) {
+            const size_t slot1 = mergeSlots ? W.maxSlots : slot0 + 1;
+            if (!generate(W, slot0, slot1)) break;
+            if (W.cands.empty()) continue;
+            ++gpuCalls;
+            refinedMax = std::max(refinedMax, (long)W.cands.size());
+            std::vector<Patch *> batch(W.cpatch.size());
+            for (size_t k = 0; k < W.cpatch.size(); ++k) batch[k] = &W.cpatch[k];
+            if (!refineBatch(batch, refineFlags, &W.parentCams)) return false;
+            commit(W);
+        }
+        finishRound(W, round);
     }
+
     printf("expansion host seconds: pop %.3f generate %.3f commit %.3f auto_save %.3f; gpu calls %ld (largest %ld candidates)\n", tPop, tGen, tCommit,
            tSave, gpuCalls, refinedMax);
     setNeighborRadius();
