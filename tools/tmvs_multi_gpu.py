@@ -1,7 +1,7 @@
 """`tmvs -r` end to end on 1, 2, 4, 8 GPUs of one box: one synthetic NVM scene with many views and a fine cell grid
 (>= 16 views, ~10^6 accepted patches), the C++ driver run with --gpus N for each N. Prints, per N, the driver's phase timers (host
 pop / generate / commit, GPU seconds, context creation) so the scaling limiter is named by measurement.
-usage: python tools/tmvs_multi_gpu.py [views width height cell round gpus_csv]"""
+usage: python tools/tmvs_multi_gpu.py [views width height cell round gpus_csv [extra driver flags, e.g. --no-pipeline]]"""
 import os
 import re
 import subprocess
@@ -20,12 +20,13 @@ h = int(sys.argv[3]) if len(sys.argv) > 3 else 1200
 cell = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 rnd = sys.argv[5] if len(sys.argv) > 5 else "8192"
 gpus = [int(g) for g in (sys.argv[6] if len(sys.argv) > 6 else "1,2,4,8").split(",")]
+extra = sys.argv[7:]
 cfg = abi.readme_config()
 cfg.maxLOD = 2
 cfg.cellSize = cell
 t0 = time.time()
 sc = scene.SynthScene(cfg, nviews=views, width=w, height=h, seed=1234, arc_deg=30.0)
-print("scene: %d views %dx%d, cellSize %d (%.1f s to synthesise)" % (views, w, h, cell, time.time() - t0), flush=True)
+print("scene: %d views %dx%d, cellSize %d (%.1f s to synthesise) driver flags %s" % (views, w, h, cell, time.time() - t0, extra), flush=True)
 rows = []
 with tempfile.TemporaryDirectory() as d:
     path = mvsio.write_nvm_scene(d, sc, n_seeds=256)
@@ -33,7 +34,7 @@ with tempfile.TemporaryDirectory() as d:
     for g in gpus:
         t0 = time.time()
         r = subprocess.run([os.path.join(ROOT, "pais-mvs_b200", "bin", "tmvs"), "-r", path, "--config", os.path.join(d, "config.txt"),
-                            "--out-dir", d, "--round", rnd, "--gpus", str(g)], cwd=d, capture_output=True, text=True)
+                            "--out-dir", d, "--round", rnd, "--gpus", str(g)] + extra, cwd=d, capture_output=True, text=True)
         wall = time.time() - t0
         out = r.stdout
         m = re.search(r"expansion host seconds: pop ([\d.]+) generate ([\d.]+) commit ([\d.]+) auto_save ([\d.]+); gpu calls (\d+)", out)
