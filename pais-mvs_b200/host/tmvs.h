@@ -13,9 +13,13 @@
 #ifndef TMVS_HOST_H
 #define TMVS_HOST_H
 
+#include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
+#include <queue>
 #include <set>
 #include <string>
 #include <vector>
@@ -58,14 +62,79 @@ struct Patch {
     std::vector<double> imgPoint;      /* 2 per entry */
 };
 
+/* The patch ids of one cell (the reference keeps a std::vector<int> per cell, cellmap.h). Cells hold a handful of ids
+ * (maxCellPatchNum = 3 by default), and a reconstruction touches millions of them: up to five ids live inline in the 24
+ * bytes a vector header would take — no allocation, one cache line per visit — more move to the heap. */
+class CellIds {
+    int32_t w_[6];                       /* w_[0]: count; inline: ids in w_[1..5]; heap: std::vector<int>* in w_[2..3] */
+    enum { INLINE = 5 };
+    std::vector<int> *heap() const {
+        std::vector<int> *h;
+        memcpy(&h, &w_[2], sizeof(h));
+        return h;
+    }
+    void setHeap(std::vector<int> *h) { memcpy(&w_[2], &h, sizeof(h)); }
+    bool onHeap() const { return w_[0] > INLINE; }
+
+public:
+    CellIds() { w_[0] = 0; }
+    CellIds(const CellIds &o) {
+        memcpy(w_, o.w_, sizeof(w_));
+        if (o.onHeap()) setHeap(new std::vector<int>(*o.heap()));
+    }
+    CellIds &operator=(const CellIds &o) {
+        if (this == &o) return *this;
+        if (onHeap()) delete heap();
+        memcpy(w_, o.w_, sizeof(w_));
+        if (o.onHeap()) setHeap(new std::vector<int>(*o.heap()));
+        return *this;
+    }
+    ~CellIds() {
+        if (onHeap()) delete heap();
+    }
+    size_t size() const { return (size_t)w_[0]; }
+    bool empty() const { return w_[0] == 0; }
+    const int *begin() const { return onHeap() ? heap()->data() : &w_[1]; }
+    const int *end() const { return begin() + w_[0]; }
+    int operator[](size_t i) const { return begin()[i]; }
+    void push_back(int id) {
+        if (w_[0] < INLINE) { w_[1 + w_[0]++] = id; return; }
+        if (w_[0] == INLINE) {
+            std::vector<int> *h = new std::vector<int>(&w_[1], &w_[1] + INLINE);
+            setHeap(h);
+        }
+        heap()->push_back(id);
+        ++w_[0];
+    }
+    bool erase(int id) {                 /* first occurrence, order kept (std::find + vector::erase in the reference) */
+        const int *b = begin(), *e = end(), *it = std::find(b, e, id);
+        if (it == e) return false;
+        const size_t at = (size_t)(it - b);
+        if (onHeap()) {
+            std::vector<int> *h = heap();
+            h->erase(h->begin() + (long)at);
+            if ((int)h->size() == INLINE) {                 /* back inline */
+                int tmp[INLINE];
+                for (int k = 0; k < INLINE; ++k) tmp[k] = (*h)[(size_t)k];
+                delete h;
+                for (int k = 0; k < INLINE; ++k) w_[1 + k] = tmp[k];
+            }
+        } else {
+            for (size_t k = at; k + 1 < (size_t)w_[0]; ++k) w_[1 + k] = w_[2 + k];
+        }
+        --w_[0];
+        return true;
+    }
+};
+
 struct CellMap {   /* TMVS/mvs/cellmap.{h,cpp} */
     int width = 0, height = 0;
-    std::vector<std::vector<int> > cells;
+    std::vector<CellIds> cells;
     void init(int imgW, int imgH, int cellSize);
     bool inMap(int x, int y) const { return !(x < 0 || y < 0 || x >= width || y >= height); }
     bool insert(int x, int y, int id);
     bool drop(int x, int y, int id);
-    const std::vector<int> &cell(int x, int y) const { return cells[(size_t)y * width + x]; }
+    const CellIds &cell(int x, int y) const { return cells[(size_t)y * width + x]; }
 };
 
 void setInitConfig(MvsConfig &c);                                   /* TMVS.cpp:26-52 */
@@ -137,7 +206,7 @@ public:
     void setNeighborRadius();                                       /* mvs.cpp:147-152 */
     bool runtimeFiltering(const Patch &p) const;                    /* mvs.cpp:838-898 */
     void getExpansionPatchCenter(const Camera &cam, const Patch &parent, int cx, int cy, double center[3]) const;   /* mvs.cpp:809-836 */
-    bool skipNeighborCell(const std::vector<int> &cell, const Patch &ref) const;                                    /* mvs.cpp:792-807 */
+    bool skipNeighborCell(const CellIds &cell, const Patch &ref) const;                                    /* mvs.cpp:792-807 */
     static bool isNeighbor(const Patch &a, const Patch &b, double neighborRadius);                                  /* patch.cpp:6-23 */
     int getPatchIdFromQueue();                                      /* mvs.cpp:636-788, indexed */
     size_t byPriorityQueueSize() const { return prioQueue.size() > fifo.size() ? prioQueue.size() : fifo.size(); }
@@ -165,7 +234,10 @@ private:
         }
         return id >= 0 && (size_t)id < idIndex.size() ? idIndex[id] : nullptr;
     }
-    std::set<std::pair<std::pair<double, long>, int> > prioQueue;
+    /* min-heap on (key, insertion sequence): the same total order an ordered set would give (sequence numbers are unique),
+     * with O(1) average insertion into a contiguous array */
+    typedef std::pair<std::pair<double, long>, int> PrioEntry;
+    std::priority_queue<PrioEntry, std::vector<PrioEntry>, std::greater<PrioEntry> > prioQueue;
     std::deque<int> fifo;
     long queueSeq = 0;
     std::vector<pmvs_ctx *> ctxs;       /* one per GPU */

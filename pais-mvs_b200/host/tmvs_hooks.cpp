@@ -164,7 +164,7 @@ int tmvs_hook_cell(void *h, int cam, int cx, int cy, int *out, int cap) {   /* -
     const MVS &m = *(MVS *)h;
     const CellMap &cm = m.cellMaps[cam];
     if (!cm.inMap(cx, cy)) return -1;
-    const std::vector<int> &c = cm.cell(cx, cy);
+    const CellIds &c = cm.cell(cx, cy);
     for (int k = 0; k < (int)c.size() && k < cap; ++k) out[k] = c[k];
     return (int)c.size();
 }

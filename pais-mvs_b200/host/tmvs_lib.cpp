@@ -159,7 +159,7 @@ bool Camera::project(const double X[3], double out[2], int LOD, double lodRatio)
     const double z2 = (R[6] * X[0] + R[7] * X[1] + R[8] * X[2]) + t[2];
     out[0] = focal[0] * (x2 / z2) + principal[0];
     out[1] = focal[1] * (y2 / z2) + principal[1];
-    const double sc = pow(lodRatio, LOD);
+    const double sc = LOD == 0 ? 1.0 : pow(lodRatio, LOD);      /* pow(x, 0) == 1 exactly */
     out[0] *= sc;
     out[1] *= sc;
     if (LOD > maxLOD || std::isnan(out[0]) || std::isnan(out[1])) return false;   /* camera.h:116-131 */
@@ -217,7 +217,7 @@ bool MVS::addCamera(Camera &cam, bool loadImage) {
 void CellMap::init(int imgW, int imgH, int cellSize) {
     width = (int)std::ceil((double)imgW / (double)cellSize);
     height = (int)std::ceil((double)imgH / (double)cellSize);
-    cells.assign((size_t)width * height, std::vector<int>());
+    cells.assign((size_t)width * height, CellIds());
 }
 bool CellMap::insert(int x, int y, int id) {
     if (!inMap(x, y)) return false;
@@ -226,11 +226,7 @@ bool CellMap::insert(int x, int y, int id) {
 }
 bool CellMap::drop(int x, int y, int id) {
     if (!inMap(x, y)) return false;
-    std::vector<int> &c = cells[(size_t)y * width + x];
-    std::vector<int>::iterator it = std::find(c.begin(), c.end(), id);
-    if (it == c.end()) return false;
-    c.erase(it);
-    return true;
+    return cells[(size_t)y * width + x].erase(id);
 }
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -401,7 +397,7 @@ bool MVS::runtimeFiltering(const Patch &p) const {   /* mvs.cpp:838-898 */
         const int cx = (int)(p.imgPoint[2 * i] / cfg.cellSize), cy = (int)(p.imgPoint[2 * i + 1] / cfg.cellSize);
         const CellMap &m = cellMaps[p.camIdx[i]];
         if (!m.inMap(cx, cy)) continue;   /* the reference indexes the cell unchecked */
-        const std::vector<int> &cell = m.cell(cx, cy);
+        const CellIds &cell = m.cell(cx, cy);
         if (std::find(cell.begin(), cell.end(), p.id) != cell.end()) return true;
         if ((int)cell.size() >= cfg.maxCellPatchNum) ++fullCellCounter;
     }
@@ -422,7 +418,7 @@ void MVS::getExpansionPatchCenter(const Camera &cam, const Patch &parent, int cx
     for (int c = 0; c < 3; ++c) center[c] = cam.center[c] + u * v12[c];
 }
 
-bool MVS::skipNeighborCell(const std::vector<int> &cell, const Patch &ref) const {   /* mvs.cpp:792-807 */
+bool MVS::skipNeighborCell(const CellIds &cell, const Patch &ref) const {   /* mvs.cpp:792-807 */
     const int n = (int)cell.size();
     if (n >= cfg.maxCellPatchNum) return true;
     for (int k = 0; k < n; ++k) {
@@ -446,10 +442,12 @@ void MVS::setCellMaps() {   /* mvs.cpp:116-133 (+ initCellMaps :74-88) */
 
 void MVS::insertPatch(const Patch &p) {   /* mvs.cpp:579-601 */
     if (!runtimeFiltering(p)) return;
-    const std::pair<std::map<int, Patch>::iterator, bool> ins = patches.insert(std::pair<int, Patch>(p.id, p));
-    if (!idIndex.empty() && ins.second && p.id >= 0) {        /* keep the id index of a running expansion current */
+    /* ids grow monotonically during an expansion: the end() hint makes the insertion O(1) */
+    const size_t before = patches.size();
+    const std::map<int, Patch>::iterator ins = patches.insert(patches.end(), std::pair<int, Patch>(p.id, p));
+    if (!idIndex.empty() && patches.size() != before && p.id >= 0) {        /* keep the id index of a running expansion current */
         if ((size_t)p.id >= idIndex.size()) idIndex.resize(std::max((size_t)p.id + 1, idIndex.size() * 2), nullptr);
-        idIndex[p.id] = &ins.first->second;
+        idIndex[p.id] = &ins->second;
     }
     queuePush(p.id);
     for (size_t i = 0; i < p.camIdx.size() && 2 * i + 1 < p.imgPoint.size(); ++i)
@@ -476,20 +474,20 @@ void MVS::deletePatch(int id) {   /* mvs.cpp:607-634 */
  * lazily when they surface, like the reference erases them while scanning. */
 void MVS::queuePush(int id) {
     queue.push_back(id);
-    std::map<int, Patch>::const_iterator it = patches.find(id);
-    const double pr = it == patches.end() ? 0.0 : it->second.priority;
+    const Patch *qp = lookup(id);
+    const double pr = qp ? qp->priority : 0.0;
     const double key = cfg.expansionStrategy == EXPANSION_WORST_FIRST ? -pr : pr;
     /* never selected by the strict comparisons against the initial +-DBL_MAX (:682, :717): NaN; DBL_MAX and above under
      * best-first; -DBL_MAX and below under worst-first */
     const bool selectable = !std::isnan(pr) && (cfg.expansionStrategy == EXPANSION_WORST_FIRST ? pr > -DBL_MAX : pr < DBL_MAX);
-    if (selectable) prioQueue.insert(std::make_pair(std::make_pair(key, queueSeq), id));
+    if (selectable) prioQueue.push(std::make_pair(std::make_pair(key, queueSeq), id));
     fifo.push_back(id);
     ++queueSeq;
 }
 
 void MVS::queueClear() {
     queue.clear();
-    prioQueue.clear();
+    prioQueue = decltype(prioQueue)();
     fifo.clear();
     queueSeq = 0;
 }
@@ -500,15 +498,15 @@ int MVS::getPatchIdFromQueue() {
         int id;
         if (byPriority) {
             if (prioQueue.empty()) return -1;
-            id = prioQueue.begin()->second;
-            prioQueue.erase(prioQueue.begin());
+            id = prioQueue.top().second;
+            prioQueue.pop();
         } else {
             if (fifo.empty()) return -1;
             if (cfg.expansionStrategy == EXPANSION_BREATH_FIRST) { id = fifo.front(); fifo.pop_front(); }
             else { id = fifo.back(); fifo.pop_back(); }
         }
-        std::map<int, Patch>::const_iterator it = patches.find(id);
-        if (it == patches.end() || it->second.expanded) continue;
+        const Patch *qp = lookup(id);
+        if (!qp || qp->expanded) continue;
         return id;
     }
 }
@@ -689,18 +687,18 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     size_t saveTime = 0;
     struct Cand { int parent, cam, cx, cy; };
     typedef std::chrono::steady_clock Clock;
-    double tPop = 0, tGen = 0, tCommit = 0, tSave = 0;
+    double tPop = 0, tGen = 0, tGenOpen = 0, tCommit = 0, tSave = 0;
     Clock::time_point lastSave = Clock::now();
     long gpuCalls = 0, refinedMax = 0;
     /* per-pass scratch over the cell maps, reset lazily by a pass stamp: candidates already generated for a cell, and
      * (merged mode) the chain of candidates expected to land in it */
-    struct CellScratch { std::vector<int> stamp, pend, head; };
+    struct CellRec { int stamp, pend, head; };     /* one record per cell: one cache line per visit */
+    typedef std::vector<CellRec> CellScratch;
     std::vector<CellScratch> scratch(cameras.size());
     for (size_t i = 0; i < cameras.size(); ++i) {
         const size_t nc = (size_t)cellMaps[i].width * cellMaps[i].height;
-        scratch[i].stamp.assign(nc, -1);
-        scratch[i].pend.assign(nc, 0);
-        scratch[i].head.assign(nc, -1);
+        const CellRec fresh = {-1, 0, -1};
+        scratch[i].assign(nc, fresh);
     }
     std::vector<std::pair<int, int> > chain;       /* (candidate index, next entry) */
     int passStamp = 0;
@@ -724,24 +722,24 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
         /* 1. pop up to roundSize parents in strategy order */
         Clock::time_point tp0 = Clock::now();
         for (size_t k = 0; k < carry.size(); ++k)
-            if (patches.find(carry[k].parent) != patches.end()) { W.parents.push_back(carry[k].parent); W.tried.push_back(carry[k].tried); }
+            if (lookup(carry[k].parent)) { W.parents.push_back(carry[k].parent); W.tried.push_back(carry[k].tried); }
         carry.clear();
         const size_t nCarried = W.parents.size();
         while ((int)(W.parents.size() - nCarried) < roundSize) {
             const int id = getPatchIdFromQueue();
             if (id < 0) break;
-            std::map<int, Patch>::iterator it = patches.find(id);
-            if (it == patches.end()) continue;
-            it->second.expanded = true;
-            if (!runtimeFiltering(it->second)) { deletePatch(id); continue; }   /* mvs.cpp:255-260 */
+            Patch *pp = const_cast<Patch *>(lookup(id));
+            if (!pp) continue;
+            pp->expanded = true;
+            if (!runtimeFiltering(*pp)) { deletePatch(id); continue; }   /* mvs.cpp:255-260 */
             W.parents.push_back(id);
         }
         tPop += std::chrono::duration<double>(Clock::now() - tp0).count();
         if (W.parents.empty()) return;
         W.maxSlots = 0;
         for (size_t k = 0; k < W.parents.size(); ++k) {
-            std::map<int, Patch>::const_iterator pit = patches.find(W.parents[k]);
-            if (pit != patches.end()) W.maxSlots = std::max(W.maxSlots, pit->second.camIdx.size());
+            const Patch *pp = lookup(W.parents[k]);
+            if (pp) W.maxSlots = std::max(W.maxSlots, pp->camIdx.size());
         }
         W.tried.resize(W.parents.size());
         for (size_t k = 0; k < W.parents.size(); ++k) W.tried[k].resize(W.maxSlots * 4, 0);
@@ -777,8 +775,8 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             chain.clear();
             auto cellAt = [&](int cam, int x, int y) -> size_t {
                 const size_t idx = (size_t)y * cellMaps[cam].width + x;
-                CellScratch &sc = scratch[cam];
-                if (sc.stamp[idx] != passStamp) { sc.stamp[idx] = passStamp; sc.pend[idx] = 0; sc.head[idx] = -1; }
+                CellRec &sc = scratch[cam][idx];
+                if (sc.stamp != passStamp) { sc.stamp = passStamp; sc.pend = 0; sc.head = -1; }
                 return idx;
             };
             /* the read-only part of the visit — is the neighbour cell inside the map and not to be skipped
@@ -788,9 +786,9 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             std::vector<unsigned char> open(W.parents.size() * nSl * 4, 0);
 #pragma omp parallel for schedule(dynamic, 32) if (W.parents.size() >= 128)
             for (long k = 0; k < (long)W.parents.size(); ++k) {
-                std::map<int, Patch>::const_iterator pit = patches.find(W.parents[k]);
-                if (pit == patches.end()) continue;
-                const Patch &pth = pit->second;
+                const Patch *pp = lookup(W.parents[k]);          /* O(1) id index: a std::map walk per (slot, parent) was the largest host cost */
+                if (!pp) continue;
+                const Patch &pth = *pp;
                 for (size_t slot = slot0; slot < slot1; ++slot) {
                     if (slot >= pth.camIdx.size() || 2 * slot + 1 >= pth.imgPoint.size()) continue;
                     const CellMap &m = cellMaps[pth.camIdx[slot]];
@@ -800,12 +798,13 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                         open[((size_t)k * nSl + (slot - slot0)) * 4 + j] = m.inMap(nx[j], ny[j]) && !skipNeighborCell(m.cell(nx[j], ny[j]), pth);
                 }
             }
+            tGenOpen += std::chrono::duration<double>(Clock::now() - tg0).count();
             bool anySlot = false;
             for (size_t slot = slot0; slot < slot1; ++slot)
             for (size_t k = 0; k < W.parents.size(); ++k) {
-                std::map<int, Patch>::const_iterator pit = patches.find(W.parents[k]);
-                if (pit == patches.end()) continue;
-                const Patch &pth = pit->second;
+                const Patch *pp = lookup(W.parents[k]);          /* O(1) id index: a std::map walk per (slot, parent) was the largest host cost */
+                if (!pp) continue;
+                const Patch &pth = *pp;
                 if (slot >= pth.camIdx.size() || 2 * slot + 1 >= pth.imgPoint.size()) continue;
                 anySlot = true;
                 const int ci = pth.camIdx[slot];
@@ -816,11 +815,11 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                     if (!open[(k * nSl + (slot - slot0)) * 4 + j]) continue;
                     if (W.tried[k][slot * 4 + j]) continue;
                     const size_t cellIdx = cellAt(ci, nx[j], ny[j]);
-                    int &pend = scratch[ci].pend[cellIdx];
+                    int &pend = scratch[ci][cellIdx].pend;
                     if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
                     if (mergeSlots) {
                         bool taken = false;
-                        for (int q = scratch[ci].head[cellIdx]; q >= 0 && !taken; q = chain[q].second)
+                        for (int q = scratch[ci][cellIdx].head; q >= 0 && !taken; q = chain[q].second)
                             taken = isNeighbor(pth, W.cpatch[chain[q].first], cfg.neighborRadius);
                         if (taken) continue;
                     }
@@ -846,8 +845,8 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                             const int ex = (int)(pt[0] / cfg.cellSize), ey = (int)(pt[1] / cfg.cellSize);
                             if (!cellMaps[cv].inMap(ex, ey)) continue;
                             const size_t eIdx = cellAt(cv, ex, ey);
-                            chain.push_back(std::make_pair((int)W.cpatch.size() - 1, scratch[cv].head[eIdx]));
-                            scratch[cv].head[eIdx] = (int)chain.size() - 1;
+                            chain.push_back(std::make_pair((int)W.cpatch.size() - 1, scratch[cv][eIdx].head));
+                            scratch[cv][eIdx].head = (int)chain.size() - 1;
                         }
                 }
             }
@@ -860,9 +859,9 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
         {
             Clock::time_point tc0 = Clock::now();
             for (size_t k = 0; k < W.cands.size(); ++k) {
-                std::map<int, Patch>::const_iterator pit = patches.find(W.cands[k].parent);
-                if (pit == patches.end()) continue;
-                if (skipNeighborCell(cellMaps[W.cands[k].cam].cell(W.cands[k].cx, W.cands[k].cy), pit->second)) continue;
+                const Patch *pp = lookup(W.cands[k].parent);
+                if (!pp) continue;
+                if (skipNeighborCell(cellMaps[W.cands[k].cam].cell(W.cands[k].cx, W.cands[k].cy), *pp)) continue;
                 const size_t before = patches.size();
                 insertPatch(W.cpatch[k]);
                 W.accepted += patches.size() - before;
@@ -913,8 +912,8 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 Clock::time_point tg0 = Clock::now();
                 size_t keep = 0;
                 for (size_t k = 0; k < next.cands.size(); ++k) {
-                    std::map<int, Patch>::const_iterator pit = patches.find(next.cands[k].parent);
-                    if (pit == patches.end() || skipNeighborCell(cellMaps[next.cands[k].cam].cell(next.cands[k].cx, next.cands[k].cy), pit->second)) continue;
+                    const Patch *pp = lookup(next.cands[k].parent);
+                    if (!pp || skipNeighborCell(cellMaps[next.cands[k].cam].cell(next.cands[k].cx, next.cands[k].cy), *pp)) continue;
                     if (keep != k) {
                         next.cands[keep] = next.cands[k];
                         next.cpatch[keep] = next.cpatch[k];
@@ -957,6 +956,7 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
 
     printf("expansion host seconds: pop %.3f generate %.3f commit %.3f auto_save %.3f; gpu calls %ld (largest %ld candidates)\n", tPop, tGen, tCommit,
            tSave, gpuCalls, refinedMax);
+    if (verbose || getenv("TMVS_HOST_TIMERS")) printf("generate: %.3f s of it in the parallel open-cell scan\n", tGenOpen);
     setNeighborRadius();
     return true;
 }
@@ -986,7 +986,7 @@ void MVS::cellFiltering() {   /* mvs.cpp:279-325 */
         CellMap &map = cellMaps[i];
         for (int x = 0; x < map.width; ++x)
             for (int y = 0; y < map.height; ++y) {
-                const std::vector<int> &cell = map.cell(x, y);
+                const CellIds &cell = map.cell(x, y);
                 const int pthNum = (int)cell.size();
                 std::vector<int> removeIdx;
                 for (int j = 0; j < pthNum; ++j) {
@@ -1013,7 +1013,7 @@ void MVS::neighborCellFiltering(double neighborRatio) {   /* mvs.cpp:327-397 */
         CellMap &map = cellMaps[i];
         for (int x = 0; x < map.width; ++x)
             for (int y = 0; y < map.height; ++y) {
-                const std::vector<int> &cell = map.cell(x, y);
+                const CellIds &cell = map.cell(x, y);
                 std::vector<int> removeIdx;
                 const int nx[9] = {x, x - 1, x + 1, x - 1, x + 1, x + 1, x, x - 1, x};
                 const int ny[9] = {y, y - 1, y - 1, y + 1, y + 1, y, y + 1, y, y - 1};
@@ -1025,7 +1025,7 @@ void MVS::neighborCellFiltering(double neighborRatio) {   /* mvs.cpp:327-397 */
                     int neighborPthSum = 0, neighborPthNum = 0;
                     for (int q = 0; q < 9; ++q) {
                         if (!map.inMap(nx[q], ny[q])) continue;
-                        const std::vector<int> &neighborCell = map.cell(nx[q], ny[q]);
+                        const CellIds &neighborCell = map.cell(nx[q], ny[q]);
                         neighborPthSum += (int)neighborCell.size();
                         for (size_t k = 0; k < neighborCell.size(); ++k) {
                             const Patch *pn = lookup(neighborCell[k]);
@@ -1054,7 +1054,7 @@ void MVS::visibilityFiltering() {   /* mvs.cpp:399-446 */
             const int cx = (int)(pth.imgPoint[2 * i] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * i + 1] / cfg.cellSize);
             const CellMap &map = cellMaps[pth.camIdx[i]];
             if (!map.inMap(cx, cy)) continue;          /* the reference indexes the cell unchecked (out of range there is undefined) */
-            const std::vector<int> &cell = map.cell(cx, cy);
+            const CellIds &cell = map.cell(cx, cy);
             for (size_t p = 0; p < cell.size(); ++p) {
                 if (cell[p] == pth.id) continue;
                 const Patch *pn = lookup(cell[p]);

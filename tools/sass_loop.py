@@ -1,5 +1,5 @@
 """Opcode histogram of the largest loop of a device function inside libpmvs_b200.so (no GPU needed).
-usage: python tools/sass_loop.py <substring of the function label> [kernel substring]"""
+usage: python tools/sass_loop.py <substring of the function label> [kernel substring [loop index]]   (SASS_DUMP=1 prints the loop)"""
 import collections
 import os
 import re
@@ -30,7 +30,9 @@ for i, l in enumerate(body):
     if m and m.group(1) in labels and labels[m.group(1)] < i:
         loops.append((labels[m.group(1)], i))
 print("function lines", len(body), "loops", loops)
-a, b = max(loops, key=lambda t: t[1] - t[0])
+a, b = loops[int(sys.argv[3])] if len(sys.argv) > 3 else max(loops, key=lambda t: t[1] - t[0])
+if os.environ.get("SASS_DUMP"):
+    print("\n".join(body[a:b + 1]))
 ops = collections.Counter()
 for l in body[a:b + 1]:
     m = re.search(r"\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
