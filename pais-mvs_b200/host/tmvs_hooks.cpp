@@ -70,7 +70,8 @@ int planeRefine(void *user, int n, const PmvsPatchIn *in, PmvsPatchOut *out, uns
 
 extern "C" {
 
-/* runs MVS::expansionPatches over the patches put so far with the plane stand-in; returns the number of refine calls */
+/* runs MVS::expansionPatches over the patches put so far with the plane stand-in; returns the number of refine calls.
+ * mergeSlots: 0 one pass per camera slot, 1 merged pass with pipelined rounds (the default of tmvs), 2 merged pass, --no-pipeline */
 long tmvs_hook_expand_plane(void *h, double planeZ, int roundSize, int mergeSlots, long *refined) {
     MVS &m = *(MVS *)h;
     PlaneRefiner r;
@@ -80,6 +81,7 @@ long tmvs_hook_expand_plane(void *h, double planeZ, int roundSize, int mergeSlot
     m.refineUser = &r;
     m.roundSize = roundSize;
     m.mergeSlots = mergeSlots != 0;
+    m.pipelineRounds = mergeSlots != 2;
     m.autosaveSeconds = 1e18;
     const bool ok = m.expansionPatches();
     m.refineOverride = nullptr;

@@ -110,7 +110,7 @@ def test_rounds_and_merged_pass_grow_the_same_surface(hooks, cfg):
     serial, _ = oracle_expand(base)
     cov0 = coverage(base, serial)
     results = {}
-    for rnd, merge in ((16, False), (16, True), (64, True), (1024, True)):
+    for rnd, merge in ((16, False), (16, True), (64, True), (1024, True), (64, 2)):      # merge 2: merged pass without pipelined rounds
         P = seeded_pair(hooks, cfg, seed=77)
         got, calls, refined = host_expand(P, rnd, merge)
         results[(rnd, merge)] = (len(got), calls, refined)
@@ -124,13 +124,16 @@ def test_rounds_and_merged_pass_grow_the_same_surface(hooks, cfg):
     # one merged pass per round: fewer calls than one per camera slot, and no more refinements
     assert results[(16, True)][1] < results[(16, False)][1] and results[(16, True)][2] <= results[(16, False)][2]
     assert results[(1024, True)][1] < results[(64, True)][1] < results[(16, True)][1]
+    # pipelined rounds generate round k+1 before commit k and prune afterwards: about the work of the unpipelined loop
+    assert results[(64, True)][2] <= 1.1 * results[(64, 2)][2]
     base.close()
 
 
-def test_expansion_is_deterministic(hooks, cfg):
+@pytest.mark.parametrize("merge", [1, 2])
+def test_expansion_is_deterministic(hooks, cfg, merge):
     runs = []
     for _ in range(2):
         P = seeded_pair(hooks, cfg, seed=5)
-        runs.append(host_expand(P, 64, True))
+        runs.append(host_expand(P, 64, merge))
         P.close()
     assert runs[0] == runs[1]
