@@ -526,7 +526,7 @@ static int apply_config(pmvs_ctx *ctx, const PmvsConfig *cfg) {
     {
         const char *envVL = getenv("PMVS_VL");          /* tuning / A-B: PMVS_VL=0 keeps the column-lane loop */
         s.useVL = (envVL && atoi(envVL) == 0) ? 0 : 1;
-        if (const char *envG = getenv("PMVS_ROWS_GLN")) s.useVL |= (atoi(envG) & 7) << 4;      /* tuning: lanes per pixel of fitness_vl_rows */
+        if (const char *envG = getenv("PMVS_ROWS_GLN")) s.useVL |= (atoi(envG) & 15) << 4;      /* tuning: lanes per pixel of fitness_vl_rows */
     }
     for (int l = 0; l < PMVS_MAX_LEVELS; ++l) s.lodScale[l] = pow(ctx->cfg.lodRatio, l);
     /* correlation scratch: one slab per resident CTA */

@@ -1478,7 +1478,7 @@ __device__ __noinline__ void fitness_vl_many(const DevScene &S, const EvalCtx &E
 }
 
 /*
- * Many views without a colour stash (fitness_vl_rows): a quad of lanes owns one window pixel at a time (8 columns per pass,
+ * Many views without a colour stash (fitness_vl_rows): a group of GLN lanes (a quad below) owns one window pixel at a time (32 / GLN columns per pass,
  * rows one after the other); lane s samples the views {4c + s} — at most 4 G4 of them — and keeps THEIR colours in
  * registers. The cross-view sum and the sum of absolute deviations are quad all-reduces (two butterfly shuffles each; the
  * pairwise order (l0 + l1) + (l2 + l3) is the same on every lane), so nothing has to be transposed or stored, one sampling
@@ -1490,7 +1490,7 @@ template <int GLN, int G4, bool GRAD>
 __device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *__restrict__ Hw,
                                              const double *__restrict__ sExpT, double &fitOut, double &swOut) {
     constexpr int NV = 4 * G4;                       /* views of one lane */
-    constexpr int LGN = GLN == 4 ? 2 : (GLN == 2 ? 1 : 0);
+    constexpr int LGN = GLN == 8 ? 3 : (GLN == 4 ? 2 : (GLN == 2 ? 1 : 0));
     const int lane = threadIdx.x & 31, s = lane & (GLN - 1), ci = lane >> LGN;
     const int V = E.V, NG = V - 1, refV = E.refView, nx = R.nx, ny = R.ny, nyp = R.nyp;
     const unsigned hA = smem_addr(Hw), xsA = smem_addr(R.xs), gxA = smem_addr(R.gx), ysgA = smem_addr(R.ysg), mkA = smem_addr(R.mask);
@@ -1568,6 +1568,7 @@ __device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E
             double sum = tree_sum<NV>(col);
             if (GLN > 1) sum += shfl_xor_f64(sum, 1);
             if (GLN > 2) sum += shfl_xor_f64(sum, 2);
+            if (GLN > 4) sum += shfl_xor_f64(sum, 4);
             const unsigned pix = 8u * (unsigned)(ic * nyp + j);
             const double cref = lds_f64(rcA + pix);
             sum += cref;
@@ -1577,6 +1578,7 @@ __device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E
             double dev = tree_sum<NV>(col);
             if (GLN > 1) dev += shfl_xor_f64(dev, 1);
             if (GLN > 2) dev += shfl_xor_f64(dev, 2);
+            if (GLN > 4) dev += shfl_xor_f64(dev, 4);
             dev += fabs(cref - mean);
             double wgt;
             if (GRAD) wgt = lds_f64(pwA + pix);                                              /* patch.cpp:1030-1032, :1036-1038, :986 */
@@ -1662,8 +1664,12 @@ __device__ __forceinline__ bool fitness_vl_dispatch(const DevScene &S, const Eva
         }
 #endif
         /* lanes per pixel: few views -> fewer lanes share a pixel (the per-pixel tail is computed by all of them) */
-        const int forced = (S.useVL >> 4) & 7;
-        const int gln = forced ? forced : (NGv <= 16 ? 1 : (NGv <= 32 ? 2 : 4));
+        const int forced = (S.useVL >> 4) & 15;
+        /* measured (profiles/r2_ab_runs.txt, run 8): the FEWEST lanes per pixel that keep a lane's colours in registers win —
+         * lanes of a group sample different views, i.e. different images, so every extra lane per pixel splits the warp's tap
+         * load into more 32-byte sectors (config 3: 14.5 / 12.8 / 8.9 k patches/s at 1 / 2 / 4 lanes, config 4: 18.9 / 16.2 /
+         * 11.9 k at 2 / 4 / 8); above 48 views 8 lanes x 8 views (no spills) edge out 4 x 16 (config 5: 3.39 vs 3.33 k) */
+        const int gln = forced ? forced : (NGv <= 16 ? 1 : (NGv <= 32 ? 2 : (NGv <= 48 ? 4 : 8)));
 #define PMVS_ROWS(GLN_, G4_) do { if (R.pw) fitness_vl_rows<GLN_, G4_, true>(S, E, R, Hw, sExpT, fit, sw); else fitness_vl_rows<GLN_, G4_, false>(S, E, R, Hw, sExpT, fit, sw); } while (0)
         if (gln == 1) {
             if (NGv <= 4) PMVS_ROWS(1, 1);
@@ -1677,11 +1683,14 @@ __device__ __forceinline__ bool fitness_vl_dispatch(const DevScene &S, const Eva
             else if (NGv <= 24) PMVS_ROWS(2, 3);
             else if (NGv <= 32) PMVS_ROWS(2, 4);
             else PMVS_ROWS(4, 4);
-        } else {
+        } else if (gln == 4) {
             if (NGv <= 16) PMVS_ROWS(4, 1);
             else if (NGv <= 32) PMVS_ROWS(4, 2);
             else if (NGv <= 48) PMVS_ROWS(4, 3);
             else PMVS_ROWS(4, 4);
+        } else {
+            if (NGv <= 32) PMVS_ROWS(8, 1);
+            else PMVS_ROWS(8, 2);
         }
 #undef PMVS_ROWS
         return true;
