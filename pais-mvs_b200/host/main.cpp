@@ -7,6 +7,7 @@
  * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
  * round, default 1024), --device D, --gpus N (shard every batch over N GPUs), --seed S (run seed of the counter-based PSO
  * RNG), --merge-slots / --slot-passes (one GPU pass per round over all camera slots, or one per slot: the reference's visiting order),
+ * --no-pipeline (merged mode: do not generate round k+1 on the host while the GPUs refine round k),
  * --autosave-seconds T (spacing of auto_save.mvs checkpoints, default 5), --no-expand, -V (verbose),
  * --convert IN OUT.{mvs,ply,psr} (load + write only: needs no GPU).
  */
@@ -104,7 +105,7 @@ int main(int argc, char **argv) {
     }
     if (mode.empty()) {   /* TMVS.cpp:183-197 */
         printf("usage: tmvs -f <input.mvs> [--config config.txt] [--out-dir DIR] [--device D] [--gpus N]\n");
-        printf("usage: tmvs -r <input.nvm|input.nvm2|input.mvs> [--config config.txt] [--out-dir DIR] [--round K] [--device D] [--gpus N] [--seed S]\n");
+        printf("usage: tmvs -r <input.nvm|input.nvm2|input.mvs> [--config config.txt] [--out-dir DIR] [--round K] [--device D] [--gpus N] [--seed S] [--slot-passes] [--no-pipeline]\n");
         return 2;
     }
     if (mode == "-v" || mode == "-a") {
