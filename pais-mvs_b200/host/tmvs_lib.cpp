@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <sstream>
 #include <thread>
 
@@ -689,19 +690,23 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     typedef std::chrono::steady_clock Clock;
     double tPop = 0, tGen = 0, tGenOpen = 0, tCommit = 0, tSave = 0;
     Clock::time_point lastSave = Clock::now();
-    long gpuCalls = 0, refinedMax = 0;
+    long gpuCalls = 0, refinedMax = 0, generatedCands = 0;
     /* per-pass scratch over the cell maps, reset lazily by a pass stamp: candidates already generated for a cell, and
-     * (merged mode) the chain of candidates expected to land in it */
-    struct CellRec { int stamp, pend, head; };     /* one record per cell: one cache line per visit */
+     * (merged mode) the chain of candidates expected to land in it. Two generations are kept: the pass being generated and
+     * the pass whose candidates are in flight on the GPUs (pipelined rounds) — what that round is expected to fill is
+     * left alone too, so a round does not refine the 3-D neighbours its predecessor is already refining */
+    struct CellRec { int stamp[2], pend[2], head[2]; };     /* one record per cell: one cache line per visit */
     typedef std::vector<CellRec> CellScratch;
     std::vector<CellScratch> scratch(cameras.size());
     for (size_t i = 0; i < cameras.size(); ++i) {
         const size_t nc = (size_t)cellMaps[i].width * cellMaps[i].height;
-        const CellRec fresh = {-1, 0, -1};
+        const CellRec fresh = {{-1, -1}, {0, 0}, {-1, -1}};
         scratch[i].assign(nc, fresh);
     }
-    std::vector<std::pair<int, int> > chain;       /* (candidate index, next entry) */
-    int passStamp = 0;
+    struct Snap { double c[3], n[3]; };             /* a candidate as generated: unrefined centre, its parent's normal */
+    std::vector<std::pair<int, int> > chain[2];    /* (candidate index, next entry) */
+    std::vector<Snap> snap[2];
+    int passStamp = 0, inflightPass = -1;
     /* merged mode: parents whose expectation failed (a candidate of theirs was rejected) try their remaining
      * (slot, neighbour) combinations in the next round's pass, like the serial reference moves on to the next camera */
     struct Carry { int parent; std::vector<unsigned char> tried; };
@@ -717,6 +722,9 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
         std::vector<Patch> cpatch;
         std::vector<std::vector<int> > parentCams;
         size_t maxSlots = 0, nCands = 0, accepted = 0;
+        int pass = -1;                                      /* stamp of the generate() pass that produced the candidates */
+        std::vector<Patch *> batch;
+        bool ok = true;
     };
     auto popParents = [&](RoundWork &W) {
         /* 1. pop up to roundSize parents in strategy order */
@@ -772,12 +780,21 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
             /* a cell can take at most maxCellPatchNum patches (skipNeighborCell, mvs.cpp:794-795): do not refine more
              * candidates for a cell than it still has room for — the serial reference would have skipped them */
             ++passStamp;
-            chain.clear();
-            auto cellAt = [&](int cam, int x, int y) -> size_t {
-                const size_t idx = (size_t)y * cellMaps[cam].width + x;
-                CellRec &sc = scratch[cam][idx];
-                if (sc.stamp != passStamp) { sc.stamp = passStamp; sc.pend = 0; sc.head = -1; }
-                return idx;
+            if (inflightPass >= 0 && ((inflightPass ^ passStamp) & 1) == 0) ++passStamp;      /* the two generations use different slots */
+            const int cs = passStamp & 1, ps = cs ^ 1;
+            chain[cs].clear();
+            snap[cs].clear();
+            auto cellAt = [&](int cam, int x, int y) -> CellRec & {
+                CellRec &sc = scratch[cam][(size_t)y * cellMaps[cam].width + x];
+                if (sc.stamp[cs] != passStamp) { sc.stamp[cs] = passStamp; sc.pend[cs] = 0; sc.head[cs] = -1; }
+                return sc;
+            };
+            auto neighborOfSnap = [&](const Patch &a, const Snap &b) -> bool {      /* isNeighbor (patch.cpp:6-23) against a snapshot */
+                const double d[3] = {a.center[0] - b.c[0], a.center[1] - b.c[1], a.center[2] - b.c[2]};
+                double dist = 0;
+                dist += fabs(dot3(d, a.normal));
+                dist += fabs(dot3(d, b.n));
+                return dist <= cfg.neighborRadius;
             };
             /* the read-only part of the visit — is the neighbour cell inside the map and not to be skipped
              * (skipNeighborCell, mvs.cpp:792-807: the patch look-ups and isNeighbor tests) — for every (parent, slot,
@@ -814,16 +831,19 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                 for (int j = 0; j < 4; ++j) {
                     if (!open[(k * nSl + (slot - slot0)) * 4 + j]) continue;
                     if (W.tried[k][slot * 4 + j]) continue;
-                    const size_t cellIdx = cellAt(ci, nx[j], ny[j]);
-                    int &pend = scratch[ci][cellIdx].pend;
-                    if ((int)m.cell(nx[j], ny[j]).size() + pend >= cfg.maxCellPatchNum) continue;
+                    CellRec &cr = cellAt(ci, nx[j], ny[j]);
+                    const bool prevLive = inflightPass >= 0 && cr.stamp[ps] == inflightPass;
+                    if ((int)m.cell(nx[j], ny[j]).size() + cr.pend[cs] + (prevLive ? cr.pend[ps] : 0) >= cfg.maxCellPatchNum) continue;
                     if (mergeSlots) {
                         bool taken = false;
-                        for (int q = scratch[ci][cellIdx].head; q >= 0 && !taken; q = chain[q].second)
-                            taken = isNeighbor(pth, W.cpatch[chain[q].first], cfg.neighborRadius);
+                        for (int q = cr.head[cs]; q >= 0 && !taken; q = chain[cs][q].second)
+                            taken = neighborOfSnap(pth, snap[cs][chain[cs][q].first]);
+                        if (prevLive)
+                            for (int q = cr.head[ps]; q >= 0 && !taken; q = chain[ps][q].second)
+                                taken = neighborOfSnap(pth, snap[ps][chain[ps][q].first]);
                         if (taken) continue;
                     }
-                    ++pend;
+                    ++cr.pend[cs];
                     Patch e;                                   /* Patch(center, parent), patch.cpp:36-43 */
                     e.type = PMVS_TYPE_EXPAND;
                     e.id = nextId++;
@@ -837,19 +857,26 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
                     W.cands.push_back(c);
                     W.cpatch.push_back(e);
                     W.parentCams.push_back(pth.camIdx);
-                    if (mergeSlots)
+                    if (mergeSlots) {
+                        Snap sn;
+                        memcpy(sn.c, e.center, sizeof(sn.c));
+                        memcpy(sn.n, pth.normal, sizeof(sn.n));
+                        snap[cs].push_back(sn);
+                        const int me = (int)snap[cs].size() - 1;
                         for (size_t v = 0; v < pth.camIdx.size(); ++v) {
                             double pt[2];
                             const int cv = pth.camIdx[v];
                             if (!cameras[cv].project(e.center, pt, 0, cfg.lodRatio)) continue;
                             const int ex = (int)(pt[0] / cfg.cellSize), ey = (int)(pt[1] / cfg.cellSize);
                             if (!cellMaps[cv].inMap(ex, ey)) continue;
-                            const size_t eIdx = cellAt(cv, ex, ey);
-                            chain.push_back(std::make_pair((int)W.cpatch.size() - 1, scratch[cv][eIdx].head));
-                            scratch[cv][eIdx].head = (int)chain.size() - 1;
+                            CellRec &er = cellAt(cv, ex, ey);
+                            chain[cs].push_back(std::make_pair(me, er.head[cs]));
+                            er.head[cs] = (int)chain[cs].size() - 1;
                         }
+                    }
                 }
             }
+            W.pass = passStamp;
             tGen += std::chrono::duration<double>(Clock::now() - tg0).count();
             return anySlot;
         }
@@ -890,51 +917,52 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
     };
     const unsigned refineFlags = PMVS_F_EXPAND_VISIBLE | PMVS_F_POST_REMOVE_INVISIBLE;     /* mvs.cpp:572-574 on the GPU */
     if (mergeSlots && pipelineRounds) {
-        RoundWork cur;
-        popParents(cur);
-        if (!cur.parents.empty()) generate(cur, 0, cur.maxSlots);
-        for (int round = 0; !cur.parents.empty(); ++round) {
-            RoundWork next;
-            if (!cur.cands.empty()) {
-                ++gpuCalls;
-                refinedMax = std::max(refinedMax, (long)cur.cands.size());
-                std::vector<Patch *> batch(cur.cpatch.size());
-                for (size_t k = 0; k < cur.cpatch.size(); ++k) batch[k] = &cur.cpatch[k];
-                bool ok = true;
-                std::thread gpu([&]() { ok = refineBatch(batch, refineFlags, &cur.parentCams); });
-                /* meanwhile: the next round's parents and candidates, from the state before this round's commit */
-                popParents(next);
-                if (!next.parents.empty()) generate(next, 0, next.maxSlots);
+        /* Two rounds in flight. While the GPUs refine round k+1 the host commits round k and then pops and generates round
+         * k+2 from that state; round k+1 itself was generated while round k was on the GPUs, knowing what round k was
+         * expected to fill (the two-generation scratch above). Nothing waits for the commit: the commit's own re-check
+         * (skipNeighborCell, mvs.cpp:792-807) turns the rare duplicate down. */
+        std::thread gpu;
+        auto launch = [&](RoundWork *W) {
+            ++gpuCalls;
+            refinedMax = std::max(refinedMax, (long)W->cands.size());
+            generatedCands += (long)W->cands.size();
+            W->batch.resize(W->cpatch.size());
+            for (size_t k = 0; k < W->cpatch.size(); ++k) W->batch[k] = &W->cpatch[k];
+            inflightPass = W->pass;
+            gpu = std::thread([this, W, refineFlags]() { W->ok = refineBatch(W->batch, refineFlags, &W->parentCams); });
+        };
+        auto popAndGenerate = [&]() -> std::unique_ptr<RoundWork> {
+            std::unique_ptr<RoundWork> W(new RoundWork());
+            popParents(*W);
+            if (!W->parents.empty()) generate(*W, 0, W->maxSlots);
+            return W;
+        };
+        std::unique_ptr<RoundWork> cur = popAndGenerate();
+        bool curLaunched = false;
+        if (!cur->cands.empty()) { launch(cur.get()); curLaunched = true; }
+        std::unique_ptr<RoundWork> next = popAndGenerate();
+        for (int round = 0; !cur->parents.empty(); ++round) {
+            if (curLaunched) {
                 gpu.join();
-                if (!ok) return false;
-                commit(cur);
-                /* prune what this commit closed: the parent is gone, or its target cell now skips (mvs.cpp:792-807) */
-                Clock::time_point tg0 = Clock::now();
-                size_t keep = 0;
-                for (size_t k = 0; k < next.cands.size(); ++k) {
-                    const Patch *pp = lookup(next.cands[k].parent);
-                    if (!pp || skipNeighborCell(cellMaps[next.cands[k].cam].cell(next.cands[k].cx, next.cands[k].cy), *pp)) continue;
-                    if (keep != k) {
-                        next.cands[keep] = next.cands[k];
-                        next.cpatch[keep] = next.cpatch[k];
-                        next.parentCams[keep].swap(next.parentCams[k]);
-                        next.candParentIdx[keep] = next.candParentIdx[k];
-                    }
-                    ++keep;
-                }
-                next.cands.resize(keep);
-                next.cpatch.resize(keep);
-                next.parentCams.resize(keep);
-                next.candParentIdx.resize(keep);
-                tGen += std::chrono::duration<double>(Clock::now() - tg0).count();
+                inflightPass = -1;
+                if (!cur->ok) return false;
             }
-            finishRound(cur, round);
-            if (next.parents.empty()) {             /* the queue was empty before this commit refilled it */
-                popParents(next);
-                if (!next.parents.empty()) generate(next, 0, next.maxSlots);
-            }
+            bool nextLaunched = false;
+            if (!next->cands.empty()) { launch(next.get()); nextLaunched = true; }
+            if (curLaunched) commit(*cur);
+            finishRound(*cur, round);
+            std::unique_ptr<RoundWork> after = popAndGenerate();
             cur = std::move(next);
+            curLaunched = nextLaunched;
+            next = std::move(after);
+            if (cur->parents.empty() && !next->parents.empty()) {      /* the queue was empty until the last commit refilled it */
+                cur = std::move(next);
+                curLaunched = false;
+                if (!cur->cands.empty()) { launch(cur.get()); curLaunched = true; }
+                next = popAndGenerate();
+            }
         }
+        if (gpu.joinable()) gpu.join();
     } else
     for (int round = 0;; ++round) {
         RoundWork W;
@@ -956,7 +984,8 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
 
     printf("expansion host seconds: pop %.3f generate %.3f commit %.3f auto_save %.3f; gpu calls %ld (largest %ld candidates)\n", tPop, tGen, tCommit,
            tSave, gpuCalls, refinedMax);
-    if (verbose || getenv("TMVS_HOST_TIMERS")) printf("generate: %.3f s of it in the parallel open-cell scan\n", tGenOpen);
+    if (verbose || getenv("TMVS_HOST_TIMERS"))
+        printf("generate: %.3f s of it in the parallel open-cell scan; pipelined rounds refined %ld candidates\n", tGenOpen, generatedCands);
     setNeighborRadius();
     return true;
 }
