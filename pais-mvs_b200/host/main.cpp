@@ -7,7 +7,7 @@
  * Extra switches (not in the reference): --config FILE, --out-dir DIR, --image-dir DIR, --round K (parents per expansion
  * round, default 1024), --device D, --gpus N (shard every batch over N GPUs), --seed S (run seed of the counter-based PSO
  * RNG), --merge-slots / --slot-passes (one GPU pass per round over all camera slots, or one per slot: the reference's visiting order),
- * --no-pipeline (merged mode: do not generate round k+1 on the host while the GPUs refine round k),
+ * --no-pipeline (merged mode: one round at a time instead of two in flight — commit k / generate k+2 overlapping GPU round k+1),
  * --autosave-seconds T (spacing of auto_save.mvs checkpoints, default 5), --no-expand, -V (verbose),
  * --convert IN OUT.{mvs,ply,psr} (load + write only: needs no GPU).
  */

@@ -711,9 +711,8 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
      * (slot, neighbour) combinations in the next round's pass, like the serial reference moves on to the next camera */
     struct Carry { int parent; std::vector<unsigned char> tried; };
     std::vector<Carry> carry;
-    /* One round's working set. Rounds are pipelined in the merged mode (below): while the GPUs refine round k's candidates the
-     * host already pops and generates round k+1 — from the state as of commit k-1 — and prunes it against commit k before it
-     * is launched (two half-rounds in flight, mvs.cpp:233-275 restructured). */
+    /* One round's working set. In the merged mode two rounds are in flight (below): the GPUs refine round k+1 while the host
+     * commits round k and pops and generates round k+2 (mvs.cpp:233-275 restructured). */
     struct RoundWork {
         std::vector<int> parents;
         std::vector<std::vector<unsigned char> > tried;     /* per parent: (slot, neighbour) combinations already refined */
