@@ -153,7 +153,7 @@ public:
     std::vector<int> queue;            /* insertion order (the reference's container) */
     int nextId = 0;
     int roundSize = 1024;              /* parents popped per expansion round */
-    bool pipelineRounds = true;        /* merged mode: generate round k+1 on the host while the GPUs refine round k */
+    bool pipelineRounds = true;        /* merged mode: two rounds in flight (commit k and generate k+2 on the host while the GPUs refine round k+1) */
     bool mergeSlots = true;            /* one GPU pass per round over all camera slots (expected-neighbour prediction); false: one per slot */
     int device = 0;                    /* first device */
     int numGpus = 1;                   /* devices device .. device+numGpus-1, candidates sharded by index */
