@@ -799,36 +799,47 @@ bool MVS::expansionPatches() {   /* mvs.cpp:233-275, 529-577 — in rounds */
              * (skipNeighborCell, mvs.cpp:792-807: the patch look-ups and isNeighbor tests) — for every (parent, slot,
              * neighbour) on all host cores; the order-dependent part below stays serial */
             const size_t nSl = slot1 - slot0;
-            std::vector<unsigned char> open(W.parents.size() * nSl * 4, 0);
+            /* per (parent, slot): camera and cell of the parent's image point + which of the four neighbour cells are open —
+             * flat arrays, so the serial pass below walks memory in order and touches a parent only for its open cells */
+            struct Visit { int cam, cx, cy; unsigned open; };
+            std::vector<Visit> visit(W.parents.size() * nSl);
+            std::vector<const Patch *> parentOf(W.parents.size());
 #pragma omp parallel for schedule(dynamic, 32) if (W.parents.size() >= 128)
             for (long k = 0; k < (long)W.parents.size(); ++k) {
                 const Patch *pp = lookup(W.parents[k]);          /* O(1) id index: a std::map walk per (slot, parent) was the largest host cost */
-                if (!pp) continue;
-                const Patch &pth = *pp;
+                parentOf[k] = pp;
                 for (size_t slot = slot0; slot < slot1; ++slot) {
+                    Visit &vs = visit[(size_t)k * nSl + (slot - slot0)];
+                    vs.cam = -1;
+                    vs.open = 0;
+                    if (!pp) continue;
+                    const Patch &pth = *pp;
                     if (slot >= pth.camIdx.size() || 2 * slot + 1 >= pth.imgPoint.size()) continue;
                     const CellMap &m = cellMaps[pth.camIdx[slot]];
                     const int cx = (int)(pth.imgPoint[2 * slot] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * slot + 1] / cfg.cellSize);
                     const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
+                    vs.cam = pth.camIdx[slot];
+                    vs.cx = cx;
+                    vs.cy = cy;
                     for (int j = 0; j < 4; ++j)
-                        open[((size_t)k * nSl + (slot - slot0)) * 4 + j] = m.inMap(nx[j], ny[j]) && !skipNeighborCell(m.cell(nx[j], ny[j]), pth);
+                        if (m.inMap(nx[j], ny[j]) && !skipNeighborCell(m.cell(nx[j], ny[j]), pth)) vs.open |= 1u << j;
                 }
             }
             tGenOpen += std::chrono::duration<double>(Clock::now() - tg0).count();
             bool anySlot = false;
             for (size_t slot = slot0; slot < slot1; ++slot)
             for (size_t k = 0; k < W.parents.size(); ++k) {
-                const Patch *pp = lookup(W.parents[k]);          /* O(1) id index: a std::map walk per (slot, parent) was the largest host cost */
-                if (!pp) continue;
-                const Patch &pth = *pp;
-                if (slot >= pth.camIdx.size() || 2 * slot + 1 >= pth.imgPoint.size()) continue;
+                const Visit &vs = visit[k * nSl + (slot - slot0)];
+                if (vs.cam < 0) continue;
                 anySlot = true;
-                const int ci = pth.camIdx[slot];
+                if (!vs.open) continue;
+                const Patch &pth = *parentOf[k];
+                const int ci = vs.cam;
                 const CellMap &m = cellMaps[ci];
-                const int cx = (int)(pth.imgPoint[2 * slot] / cfg.cellSize), cy = (int)(pth.imgPoint[2 * slot + 1] / cfg.cellSize);
+                const int cx = vs.cx, cy = vs.cy;
                 const int nx[4] = {cx - 1, cx, cx + 1, cx}, ny[4] = {cy, cy - 1, cy, cy + 1};
                 for (int j = 0; j < 4; ++j) {
-                    if (!open[(k * nSl + (slot - slot0)) * 4 + j]) continue;
+                    if (!((vs.open >> j) & 1u)) continue;
                     if (W.tried[k][slot * 4 + j]) continue;
                     CellRec &cr = cellAt(ci, nx[j], ny[j]);
                     const bool prevLive = inflightPass >= 0 && cr.stamp[ps] == inflightPass;
