@@ -207,3 +207,40 @@ int tmvs_hook_get_patch(void *h, int id, double *center, double *normal, double 
 }
 
 }   /* extern "C" */
+
+/* CellIds (tmvs.h) against std::vector<int> under random push / erase / copy traffic crossing the inline <-> heap boundary;
+ * returns 0 when every observable (size, order, contents, copies) agreed */
+extern "C" int tmvs_hook_cellids_selftest(unsigned seed, int ops) {
+    unsigned long long st = seed * 2654435761ull + 12345;
+    auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(st >> 33); };
+    CellIds c;
+    std::vector<int> model;
+    for (int k = 0; k < ops; ++k) {
+        const unsigned r = rnd() % 100;
+        if (r < 55 || model.empty()) {
+            const int id = (int)(rnd() % 12);                 /* few distinct ids: duplicates occur, erase removes the first */
+            c.push_back(id);
+            model.push_back(id);
+        } else if (r < 90) {
+            const int id = (int)(rnd() % 12);
+            const bool a = c.erase(id);
+            std::vector<int>::iterator it = std::find(model.begin(), model.end(), id);
+            const bool b = it != model.end();
+            if (b) model.erase(it);
+            if (a != b) return 1;
+        } else {
+            CellIds d(c), e;                                 /* copy construction, assignment over inline and heap states */
+            e = d;
+            e = e;
+            c = e;
+            std::vector<CellIds> v(3, c);
+            v.resize(40, CellIds());
+            c = v[2];
+        }
+        if (c.size() != model.size() || c.empty() != model.empty()) return 2;
+        for (size_t i = 0; i < model.size(); ++i)
+            if (c[i] != model[i]) return 3;
+        if ((size_t)(c.end() - c.begin()) != model.size()) return 4;
+    }
+    return 0;
+}

@@ -348,3 +348,13 @@ def test_recentering(hooks, cfg):
             assert np.allclose(list(n), p.normal, rtol=0, atol=1e-11) and np.allclose(list(s), p.normalS, rtol=0, atol=1e-11)
             assert abs(np.linalg.norm(list(n)) - 1) < 1e-14
     P.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_cell_id_container_matches_a_vector(hooks, seed):
+    """CellIds (host/tmvs.h: cell ids inline in the cell record, heap beyond five) behaves like the std::vector<int> the
+    reference keeps per cell (cellmap.h) under random push / erase-first / copy traffic across the inline <-> heap boundary."""
+    L = hooks
+    L.tmvs_hook_cellids_selftest.argtypes = [C.c_uint, C.c_int]
+    L.tmvs_hook_cellids_selftest.restype = C.c_int
+    assert L.tmvs_hook_cellids_selftest(seed, 20000) == 0
