@@ -34,8 +34,8 @@ sc2 = scene.SynthScene(cfg2, nviews=5, width=160, height=120, seed=6, tex_size=2
 with PatchRefiner(cfg2, sc2.records) as pr:
     out3 = pr.refine(sc2.patches(5, seed=3), flags=abi.F_POST_REMOVE_INVISIBLE)
     f3 = pr.fitness(scene.hypotheses_from_patches(sc2, sc2.patches(4, seed=4), cfg2, per_patch=2))
-# more than 16 views: the two-pass many-view loop; 12 views: inline x-parts instead of per-lane slots
-for nv in (18, 12):
+# many views: the rows loop with 8 (50 views), 4 (34), 2 (18) and 1 (12) lanes per pixel
+for nv in (50, 34, 18, 12):
     sc3 = scene.SynthScene(cfg2, nviews=nv, width=160, height=120, seed=7, tex_size=256, arc_deg=30.0)
     with PatchRefiner(cfg2, sc3.records) as pr:
         f4 = pr.fitness(scene.hypotheses_from_patches(sc3, sc3.patches(3, seed=5), cfg2, per_patch=2))
