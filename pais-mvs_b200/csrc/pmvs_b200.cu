@@ -891,8 +891,11 @@ static int refine_launch(pmvs_ctx *ctx, int n, const PmvsPatchIn *d_in, PmvsPatc
             if (rc) return rc;
             if (all[k].perSm < 1) continue;
             const int rounds = (P + cand[k] - 1) / cand[k];
-            /* one CTA per SM leaves a patch's serial phases (swarm bookkeeping, visibility) uncovered */
-            const double thr = (double)all[k].perSm * P / rounds * (all[k].perSm == 1 ? 0.85 : 1.0);
+            /* one CTA per SM leaves a patch's serial phases (swarm bookkeeping, visibility) uncovered — except where the
+             * scene's tables are so large (more than 48 views: ~100 KB per 8-warp CTA) that two CTAs leave the tap stream
+             * 60 KB of L1: there one 16-warp CTA (92 KB of L1) wins (config 5: 3.56 vs 3.47 k patches/s, r2_ab_runs.txt run 10) */
+            const double solo = ctx->vcap > 48 ? 1.05 : 0.85;
+            const double thr = (double)all[k].perSm * P / rounds * (all[k].perSm == 1 ? solo : 1.0);
             if (thr > bestThr + 1e-9 || (thr > bestThr - 1e-9 && bestT >= 0 && rounds < (P + cand[bestT] - 1) / cand[bestT])) { bestThr = thr; bestT = k; }
         }
         if (bestT < 0) return fail(ctx, PMVS_E_UNSUPPORTED, "refine kernel does not fit on an SM with this configuration");

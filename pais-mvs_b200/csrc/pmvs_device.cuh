@@ -1483,13 +1483,14 @@ __device__ __noinline__ void fitness_vl_many(const DevScene &S, const EvalCtx &E
  * registers. The cross-view sum and the sum of absolute deviations are quad all-reduces (two butterfly shuffles each; the
  * pairwise order (l0 + l1) + (l2 + l3) is the same on every lane), so nothing has to be transposed or stored, one sampling
  * pass, and the shared memory stays what the scene's tables need (two CTAs per SM at 64 views). The per-pixel tail
- * (weights, accumulation) is computed by all four lanes and accumulated by lane 0 of the quad: for V >= 10 it is a few
- * per cent of the pixel's work.
+ * (weights, exp, accumulation) runs on every lane of the group (lane 0 accumulates) or, at 8 lanes per pixel, once per block of
+ * 8 rows with lane s taking row s of the block.
  */
 template <int GLN, int G4, bool GRAD>
 __device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E, const RefWin &R, const double *__restrict__ Hw,
                                              const double *__restrict__ sExpT, double &fitOut, double &swOut) {
     constexpr int NV = 4 * G4;                       /* views of one lane */
+    constexpr bool SPLIT = GLN >= 8;                 /* per-pixel tail once per block of GLN rows instead of on every lane */
     constexpr int LGN = GLN == 8 ? 3 : (GLN == 4 ? 2 : (GLN == 2 ? 1 : 0));
     const int lane = threadIdx.x & 31, s = lane & (GLN - 1), ci = lane >> LGN;
     const int V = E.V, NG = V - 1, refV = E.refView, nx = R.nx, ny = R.ny, nyp = R.nyp;
@@ -1507,9 +1508,10 @@ __device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E
         const bool colOk = i < nx;
         const int ic = colOk ? i : nx - 1;
         const double x = lds_f64(xsA + 8u * ic);
-        const double gxv = (colOk && s == 0) ? (GRAD ? 1.0 : lds_f64(gxA + 8u * ic)) : 0.0;      /* lane 0 of the quad accumulates */
+        /* SPLIT: every lane accumulates the rows it ran the tail for; else lane 0 of the group accumulates */
+        const double gxv = (colOk && (SPLIT || s == 0)) ? (GRAD ? 1.0 : lds_f64(gxA + 8u * ic)) : 0.0;
         const unsigned long long mk = GRAD ? 0ull : lds_u64(mkA + 8u * ic);
-        double cfit = 0, csw = 0;
+        double cfit = 0, csw = 0, mydev = 0;
         for (int j = 0; j < ny; ++j) {
             const double y = lds_f64(ysgA + 16u * j);
             double col[NV];
@@ -1580,15 +1582,23 @@ __device__ __noinline__ void fitness_vl_rows(const DevScene &S, const EvalCtx &E
             if (GLN > 2) dev += shfl_xor_f64(dev, 2);
             if (GLN > 4) dev += shfl_xor_f64(dev, 4);
             dev += fabs(cref - mean);
-            double wgt;
-            if (GRAD) wgt = lds_f64(pwA + pix);                                              /* patch.cpp:1030-1032, :1036-1038, :986 */
-            else {
-                wgt = 0.0;
-                if ((mk >> (16 * (j & 3) + (j >> 2))) & 1ull) wgt = lds_f64(ysgA + 16u * j + 8u);
+            /* The per-pixel tail (weights, exp, accumulation) is the same on all GLN lanes of the group. SPLIT (8 lanes per pixel):
+             * instead of computing it GLN times, lane s keeps the deviation of row (block of GLN rows) + s and runs the tail once
+             * per block for ITS row. Measured (profiles/r2_ab_runs.txt, run 10): +1.6 % at 8 lanes (config 5), -2.1 % at 2 lanes
+             * (config 4: the extra live state spills), so the narrower groups keep the tail on every lane, lane 0 accumulating. */
+            if (SPLIT) {
+                if ((j & (GLN - 1)) == s) mydev = dev;
+                if ((j & (GLN - 1)) != GLN - 1 && j != ny - 1) continue;
+            } else mydev = dev;
+            const int jr = SPLIT ? (j & ~(GLN - 1)) + s : j;
+            double wgt = 0.0;
+            if (!SPLIT || jr < ny) {
+                if (GRAD) wgt = lds_f64(pwA + 8u * (unsigned)(ic * nyp + jr));                   /* patch.cpp:1030-1032, :1036-1038, :986 */
+                else if ((mk >> (16 * (jr & 3) + (jr >> 2))) & 1ull) wgt = lds_f64(ysgA + 16u * jr + 8u);
             }
-            wgt *= exp_table_c(dev * dev * negK, tabA);                                      /* patch.cpp:1033-1035 */
+            wgt *= exp_table_c(mydev * mydev * negK, tabA);                                      /* patch.cpp:1033-1035 */
             csw += wgt;
-            cfit = fma(wgt, dev, cfit);
+            cfit = fma(wgt, mydev, cfit);
         }
         sw = fma(gxv, csw, sw);
         fit = fma(gxv, cfit, fit);
