@@ -41,9 +41,9 @@ def scene_for(weights, nviews=5, radius=7, width=320, height=240, **kw):
 
 @needs_ref
 @pytest.mark.parametrize("nviews,radius,weights", [(5, 7, (0, 0, 0)), (5, 15, (1, 1, 0)), (3, 4, (1, 1, 1)), (12, 7, (1, 1, 1)), (2, 7, (1, 0, 1)),
-                                                   (20, 5, (1, 1, 0))])
+                                                   (20, 5, (1, 1, 0)), (33, 5, (1, 1, 1)), (64, 4, (1, 1, 1)), (6, 21, (1, 1, 1))])
 def test_fitness_homographies_weights_bit_exact(nviews, radius, weights):
-    cfg, sc = scene_for(weights, nviews=nviews, radius=radius, width=480 if radius > 7 else 320, height=360 if radius > 7 else 240)
+    cfg, sc = scene_for(weights, nviews=nviews, radius=radius, width=(640 if radius > 15 else 480) if radius > 7 else 320, height=(480 if radius > 15 else 360) if radius > 7 else 240)
     o = orc.Oracle(cfg, sc.records, seed=42)
     r = ref_tmvs.RefScene(cfg, sc.records, seed=42)
     assert [v.hex() for v in o.dist_weight(cfg.patchSize)] == [v.hex() for v in r.dist_weight()]
