@@ -2,7 +2,7 @@
 unmodified reference build): small scenes that exercise every branch of Patch::refine (TMVS/mvs/patch.cpp:114-176)."""
 from pmvs_b200 import abi, scene
 
-CASES = ["expand_r7", "seed_r7", "wide_arc", "occluded", "gradient_lod", "p5_defaults", "v12", "v16_p32", "r17_wide"]
+CASES = ["expand_r7", "seed_r7", "wide_arc", "occluded", "gradient_lod", "p5_defaults", "v12", "v16_p32", "r17_wide", "v34_grad"]
 
 
 def build(case):
@@ -33,6 +33,10 @@ def build(case):
         kw.update(nviews=16, arc_deg=35.0)
         cfg.particleNum, cfg.maxIteration = 32, 50
         n = 8
+    elif case == "v34_grad":            # BASELINE.json config 4 shape: more than 32 views, gradient weighting (the many-view loop, 4 lanes per pixel)
+        kw.update(nviews=34, arc_deg=30.0)
+        cfg.adaptiveGradientEnable = 1
+        n = 4
     elif case == "r17_wide":            # window wider than a warp: two column passes
         cfg.patchRadius, cfg.patchSize, cfg.distWeighting = 17, 35, 17 / 3.0
         n = 12
