@@ -594,10 +594,14 @@ bool MVS::refineBatch(std::vector<Patch *> &batch, unsigned flags, const std::ve
         r.type = p.type;
         r.id = p.id;
         const std::vector<int> &cams = parentCams ? (*parentCams)[i] : p.camIdx;
-        if (cams.size() > PMVS_MAX_VIEWS && !warnedViews) {
-#pragma omp critical
-            warnedViews = true;
-            fprintf(stderr, "tmvs: patch %d lists %zu cameras; only the first %d are used (PMVS_MAX_VIEWS)\n", p.id, cams.size(), PMVS_MAX_VIEWS);
+        if (cams.size() > PMVS_MAX_VIEWS) {
+#pragma omp critical(tmvs_warn_views)
+            {
+                if (!warnedViews) {
+                    warnedViews = true;
+                    fprintf(stderr, "tmvs: patch %d lists %zu cameras; only the first %d are used (PMVS_MAX_VIEWS)\n", p.id, cams.size(), PMVS_MAX_VIEWS);
+                }
+            }
         }
         r.nCam = (int)std::min<size_t>(cams.size(), PMVS_MAX_VIEWS);
         for (int k = 0; k < r.nCam; ++k) r.camIdx[k] = (uint16_t)cams[k];
