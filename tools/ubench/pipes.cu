@@ -9,6 +9,9 @@
 __device__ __forceinline__ double s2d(int d) { return __hiloint2double(0x43300000, (int)((uint32_t)d ^ 0x80000000u)) - (4503599627370496.0 + 2147483648.0); }
 template <int MODE, int CVT>
 __global__ void __launch_bounds__(160) k(double *out, int iters, double seed, int iseed) {
+    __shared__ double lut[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = (double)(i - 510);
+    __syncthreads();
     double a[8];
     int n[8];
 #pragma unroll
@@ -38,7 +41,8 @@ __global__ void __launch_bounds__(160) k(double *out, int iters, double seed, in
                     double c;
                     if (CVT == 0) c = fma(fy, fma(-x, (double)ndxy, (double)k1), fma(-x, (double)ndx, (double)k0));
                     else if (CVT == 1) c = fma(fy, fma(-x, (double)ndxy, s2d(k1)), fma(-x, (double)ndx, s2d(k0)));
-                    else c = fma(fy, fma(-x, s2d(ndxy), s2d(k1)), fma(-x, s2d(ndx), s2d(k0)));
+                    else if (CVT == 2) c = fma(fy, fma(-x, s2d(ndxy), s2d(k1)), fma(-x, s2d(ndx), s2d(k0)));
+                    else c = fma(fy, fma(-x, lut[ndxy + 510], (double)k1), fma(-x, lut[ndx + 510], (double)k0));   // small differences from a shared-memory table
                     a[i] = a[i] + c * 1e-9 + 1.0;
                     n[i] += 12345;
                 }
@@ -90,6 +94,7 @@ int main() {
         run<5, 0>("loop mix, 4 I2F", 1, c);
         run<5, 1>("loop mix, 2 I2F + 2 magic", 1, c);
         run<5, 2>("loop mix, 4 magic", 1, c);
+        run<5, 3>("loop mix, 2 I2F + 2 LDS table", 1, c);
     }
     return 0;
 }
